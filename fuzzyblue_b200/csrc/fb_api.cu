@@ -1,0 +1,673 @@
+// fb_api.cu — the extern "C" boundary declared in include/fuzzyblue.h: object lifetimes, the
+// per-order command stream of Atmosphere::build (src/precompute.rs:1671-2048) as stream-ordered
+// launches or a replayable CUDA graph, read-back, the renderer front-end and batches.
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device fb_builder_create fails
+// with FB_ERR_NO_DEVICE and nothing else can be constructed.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fuzzyblue.h"
+#include "fb_kernels.h"
+
+using namespace fb;
+
+static_assert(sizeof(FbParams) == 320, "FbParams must mirror the 320-byte std140 block (precompute.rs:1675)");
+static_assert(offsetof(FbParams, transmittance_mu_size) == 92, "sizes at 92");
+static_assert(offsetof(FbParams, rayleigh_density) == 128, "profiles at 128");
+static_assert(offsetof(FbParams, absorption_density) == 256, "absorption profile at 256");
+static_assert(sizeof(FbDrawParams) == 92, "FbDrawParams must mirror the 92-byte push-constant block (render.rs:231)");
+static_assert(offsetof(FbDrawParams, sun_direction) == 80, "sun_direction after the pad");
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    (void)cudaGetLastError();   // clear the sticky-less error so later calls are not poisoned
+    int st = (e == cudaErrorMemoryAllocation) ? FB_ERR_OUT_OF_MEMORY : FB_ERR_CUDA;
+    return fail(st, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+#define FB_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+const char* fb_status_string(int s) {
+    switch (s) {
+        case FB_OK: return "FB_OK";
+        case FB_ERR_INVALID_ARGUMENT: return "FB_ERR_INVALID_ARGUMENT";
+        case FB_ERR_CUDA: return "FB_ERR_CUDA";
+        case FB_ERR_OUT_OF_MEMORY: return "FB_ERR_OUT_OF_MEMORY";
+        case FB_ERR_NO_DEVICE: return "FB_ERR_NO_DEVICE";
+        case FB_ERR_NOT_READY: return "FB_ERR_NOT_READY";
+        default: return "FB_ERR_UNKNOWN";
+    }
+}
+const char* fb_last_error(void) { return g_last_error.c_str(); }
+const char* fb_version(void) { return "fuzzyblue_b200 0.1.0 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------
+// parameters
+// ---------------------------------------------------------------------------------------------
+int fb_params_default(FbParams* p) {   // src/precompute.rs:849-935
+    if (!p) return fail(FB_ERR_INVALID_ARGUMENT, "fb_params_default: NULL");
+    std::memset(p, 0, sizeof *p);
+    const float solar[3] = {1.474f, 1.850f, 1.91198f};
+    const float ray[3] = {0.005802f, 0.013558f, 0.033100f};
+    const float ozone[3] = {6.5e-4f, 1.881e-3f, 8.5e-5f};
+    for (int i = 0; i < 3; ++i) {
+        p->solar_irradiance[i] = solar[i];
+        p->rayleigh_scattering[i] = ray[i];
+        p->mie_scattering[i] = 0.003996f;
+        p->mie_extinction[i] = 0.004440f;
+        p->ground_albedo[i] = 0.1f;
+        p->absorption_extinction[i] = ozone[i];
+    }
+    p->sun_angular_radius = 0.004675f;
+    p->bottom_radius = 6360.0f;
+    p->top_radius = 6420.0f;
+    p->mie_phase_function_g = 0.8f;
+    p->mu_s_min = -0.207912f;
+    p->transmittance_mu_size = 256;
+    p->transmittance_r_size = 64;
+    p->scattering_r_size = 32;
+    p->scattering_mu_size = 128;
+    p->scattering_mu_s_size = 32;
+    p->scattering_nu_size = 8;
+    p->irradiance_mu_s_size = 64;
+    p->irradiance_r_size = 16;
+    p->rayleigh_density.layers[1].exp_term = 1.0f;
+    p->rayleigh_density.layers[1].exp_scale = -0.125f;
+    p->mie_density.layers[1].exp_term = 1.0f;
+    p->mie_density.layers[1].exp_scale = -0.833333f;
+    p->absorption_density.layers[0].width = 25.0f;
+    p->absorption_density.layers[0].linear_term = 0.066667f;
+    p->absorption_density.layers[0].constant_term = -0.666667f;
+    p->absorption_density.layers[1].linear_term = -0.066667f;
+    p->absorption_density.layers[1].constant_term = 2.666667f;
+    return FB_OK;
+}
+uint32_t fb_params_default_order(void) { return 4; }   // precompute.rs:856
+
+int fb_params_validate(const FbParams* p) {
+    if (!p) return fail(FB_ERR_INVALID_ARGUMENT, "params: NULL");
+    const int32_t s[8] = {p->transmittance_mu_size, p->transmittance_r_size, p->scattering_r_size, p->scattering_mu_size,
+                          p->scattering_mu_s_size, p->scattering_nu_size, p->irradiance_mu_s_size, p->irradiance_r_size};
+    for (int i = 0; i < 8; ++i)
+        if (s[i] < 2 || s[i] > 16384)
+            return fail(FB_ERR_INVALID_ARGUMENT, "params: every LUT size must be in [2, 16384] (x/(size-1) mappings, "
+                                                 "scattering.h:120-131)");
+    if (p->scattering_mu_size % 2) return fail(FB_ERR_INVALID_ARGUMENT, "params: scattering_mu_size must be even (scattering.h:36)");
+    if (p->scattering_mu_size > 65535 || p->scattering_r_size > 65535)
+        return fail(FB_ERR_INVALID_ARGUMENT, "params: scattering mu/r size exceeds the launch grid");
+    int64_t texels = (int64_t)p->scattering_nu_size * p->scattering_mu_s_size * p->scattering_mu_size * p->scattering_r_size;
+    if (texels > ((int64_t)1 << 31)) return fail(FB_ERR_INVALID_ARGUMENT, "params: scattering table exceeds 2^31 texels");
+    if (!(p->top_radius > p->bottom_radius) || !(p->bottom_radius > 0.f))
+        return fail(FB_ERR_INVALID_ARGUMENT, "params: need 0 < bottom_radius < top_radius");
+    return FB_OK;
+}
+int fb_params_transmittance_extent(const FbParams* p, FbExtent2D* o) {   // precompute.rs:772-777
+    if (!p || !o) return fail(FB_ERR_INVALID_ARGUMENT, "extent: NULL");
+    o->width = p->transmittance_mu_size; o->height = p->transmittance_r_size;
+    return FB_OK;
+}
+int fb_params_irradiance_extent(const FbParams* p, FbExtent2D* o) {      // :779-784
+    if (!p || !o) return fail(FB_ERR_INVALID_ARGUMENT, "extent: NULL");
+    o->width = p->irradiance_mu_s_size; o->height = p->irradiance_r_size;
+    return FB_OK;
+}
+int fb_params_scattering_extent(const FbParams* p, FbExtent3D* o) {      // :786-792
+    if (!p || !o) return fail(FB_ERR_INVALID_ARGUMENT, "extent: NULL");
+    o->width = p->scattering_nu_size * p->scattering_mu_s_size; o->height = p->scattering_mu_size; o->depth = p->scattering_r_size;
+    return FB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct FbBuilder {
+    int device;
+    int sm_count;
+    int kernels;
+    Trig trig;
+};
+
+struct FbAtmosphere {
+    int device;
+    int kernels;
+    FbParams P;
+    float4* transmittance;
+    float4* irradiance;
+    uint2* scattering;
+};
+
+struct FbPending {
+    FbBuilder* builder;
+    FbParams P;
+    uint32_t order;
+    Images img;
+    FbAtmosphere* inner;     // Option<Atmosphere>, precompute.rs:2114
+    cudaGraphExec_t graph;   // pre-recorded command stream, instantiated lazily
+    int launches;
+};
+
+struct FbRenderer {
+    int device;
+    int kernels;
+    FbDrawParams* sweep_draws;   // device copy of a sweep's draw parameters
+    uint32_t sweep_capacity;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+static size_t bytes2d(int w, int h) { return (size_t)w * h * sizeof(float4); }
+static size_t bytes3d(const FbParams& P) {
+    return (size_t)P.scattering_nu_size * P.scattering_mu_s_size * P.scattering_mu_size * P.scattering_r_size * sizeof(uint2);
+}
+static size_t image_bytes(const FbParams& P, int image) {
+    switch (image) {
+        case FB_IMAGE_TRANSMITTANCE: return bytes2d(P.transmittance_mu_size, P.transmittance_r_size);
+        case FB_IMAGE_IRRADIANCE:
+        case FB_IMAGE_DELTA_IRRADIANCE: return bytes2d(P.irradiance_mu_s_size, P.irradiance_r_size);
+        case FB_IMAGE_SCATTERING:
+        case FB_IMAGE_DELTA_RAYLEIGH:
+        case FB_IMAGE_DELTA_MIE:
+        case FB_IMAGE_SCATTERING_DENSITY:
+        case FB_IMAGE_DELTA_MULTIPLE_SCATTERING: return bytes3d(P);
+        default: return 0;
+    }
+}
+static void* image_ptr(FbPending* p, int image) {
+    switch (image) {
+        case FB_IMAGE_TRANSMITTANCE: return p->img.transmittance;
+        case FB_IMAGE_IRRADIANCE: return p->img.irradiance;
+        case FB_IMAGE_SCATTERING: return p->img.scattering;
+        case FB_IMAGE_DELTA_IRRADIANCE: return p->img.delta_irradiance;
+        case FB_IMAGE_DELTA_RAYLEIGH: return p->img.delta_rayleigh;
+        case FB_IMAGE_DELTA_MIE: return p->img.delta_mie;
+        case FB_IMAGE_SCATTERING_DENSITY: return p->img.scattering_density;
+        case FB_IMAGE_DELTA_MULTIPLE_SCATTERING: return p->img.delta_multiple_scattering;
+        default: return nullptr;
+    }
+}
+
+int fb_builder_create(int device, FbBuilder** out) {
+    if (!out) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_create: NULL out");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(FB_ERR_NO_DEVICE, "fb_builder_create: no CUDA device is visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    FB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(FB_ERR_NO_DEVICE, std::string("fb_builder_create: device '") + prop.name +
+                                          "' is not an sm_100 part; the kernels are built for sm_100a only");
+    FbBuilder* b = new (std::nothrow) FbBuilder();
+    if (!b) return fail(FB_ERR_OUT_OF_MEMORY, "fb_builder_create: host allocation");
+    b->device = device;
+    b->sm_count = prop.multiProcessorCount;
+    b->kernels = FB_KERNELS_FAST;
+    make_trig(&b->trig);
+    *out = b;
+    return FB_OK;
+}
+void fb_builder_destroy(FbBuilder* b) { delete b; }
+int fb_builder_set_kernels(FbBuilder* b, int k) {
+    if (!b || (k != FB_KERNELS_FAST && k != FB_KERNELS_REFERENCE)) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_set_kernels");
+    b->kernels = k;
+    return FB_OK;
+}
+int fb_builder_device(const FbBuilder* b) { return b ? b->device : -1; }
+int fb_builder_sm_count(const FbBuilder* b) { return b ? b->sm_count : 0; }
+
+static void free_pending_temps(FbPending* p) {
+    cudaFree(p->img.delta_irradiance);
+    cudaFree(p->img.delta_rayleigh);
+    cudaFree(p->img.delta_mie);
+    cudaFree(p->img.scattering_density);
+    cudaFree(p->img.delta_multiple_scattering);
+    cudaFree(p->img.scratch);
+    p->img.delta_irradiance = nullptr;
+    p->img.delta_rayleigh = p->img.delta_mie = p->img.scattering_density = p->img.delta_multiple_scattering = nullptr;
+    p->img.scratch = nullptr;
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+}
+
+void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
+    if (!a) return;
+    DeviceGuard g(a->device);
+    cudaFree(a->transmittance);
+    cudaFree(a->irradiance);
+    cudaFree(a->scattering);
+    delete a;
+}
+
+void fb_pending_destroy(FbPending* p) {         // Drop, precompute.rs:2122-2140
+    if (!p) return;
+    DeviceGuard g(p->builder->device);
+    free_pending_temps(p);
+    if (p->inner) fb_atmosphere_destroy(p->inner);
+    delete p;
+}
+
+int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order, FbPending** out) {
+    if (!b || !params || !out) return fail(FB_ERR_INVALID_ARGUMENT, "fb_atmosphere_allocate: NULL argument");
+    *out = nullptr;
+    int st = fb_params_validate(params);
+    if (st != FB_OK) return st;
+    if (order < 1 || order > 64) return fail(FB_ERR_INVALID_ARGUMENT, "order must be in [1, 64]");
+    DeviceGuard g(b->device);
+    if (!g.ok) return fail(FB_ERR_CUDA, "cudaSetDevice failed");
+    FbPending* p = new (std::nothrow) FbPending();
+    FbAtmosphere* a = new (std::nothrow) FbAtmosphere();
+    if (!p || !a) { delete p; delete a; return fail(FB_ERR_OUT_OF_MEMORY, "host allocation"); }
+    std::memset(&p->img, 0, sizeof p->img);
+    p->builder = b;
+    p->P = *params;
+    p->order = order;
+    p->inner = a;
+    p->graph = nullptr;
+    p->launches = 0;
+    a->device = b->device;
+    a->kernels = b->kernels;
+    a->P = *params;
+    a->transmittance = nullptr; a->irradiance = nullptr; a->scattering = nullptr;
+    // one allocation per image, as the reference does (precompute.rs:1167-1234, :589-635)
+    const size_t b2t = image_bytes(*params, FB_IMAGE_TRANSMITTANCE), b2e = image_bytes(*params, FB_IMAGE_IRRADIANCE),
+                 b3 = bytes3d(*params);
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** ptr, size_t n) { if (e == cudaSuccess) e = cudaMalloc(ptr, n); };
+    alloc((void**)&a->transmittance, b2t);
+    alloc((void**)&a->irradiance, b2e);
+    alloc((void**)&a->scattering, b3);
+    alloc((void**)&p->img.delta_irradiance, b2e);
+    alloc((void**)&p->img.delta_rayleigh, b3);
+    alloc((void**)&p->img.delta_mie, b3);
+    alloc((void**)&p->img.scattering_density, b3);
+    alloc((void**)&p->img.delta_multiple_scattering, b3);
+    p->img.scratch_bytes = fast::scratch_bytes(*params);
+    if (p->img.scratch_bytes) alloc((void**)&p->img.scratch, p->img.scratch_bytes);
+    if (e != cudaSuccess) {
+        fb_pending_destroy(p);
+        return cuda_fail(e, "cudaMalloc(image)");
+    }
+    p->img.transmittance = a->transmittance;
+    p->img.irradiance = a->irradiance;
+    p->img.scattering = a->scattering;
+    *out = p;
+    return FB_OK;
+}
+
+static LaunchCtx make_ctx(FbPending* p, cudaStream_t s) {
+    LaunchCtx c;
+    c.P = p->P;
+    c.trig = p->builder->trig;
+    c.img = p->img;
+    c.sm_count = p->builder->sm_count;
+    c.stream = s;
+    return c;
+}
+
+static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order, int r0, int r1, int* launches) {
+    const bool fastk = p->builder->kernels == FB_KERNELS_FAST;
+    cudaError_t e = cudaSuccess;
+    int n = 1;
+    switch (stage) {
+        case FB_STAGE_TRANSMITTANCE: e = fastk ? fast::transmittance(c) : ref::transmittance(c); break;
+        case FB_STAGE_DIRECT_IRRADIANCE: e = fastk ? fast::direct_irradiance(c) : ref::direct_irradiance(c); break;
+        case FB_STAGE_SINGLE_SCATTERING: e = fastk ? fast::single_scattering(c, r0, r1) : ref::single_scattering(c, r0, r1); break;
+        case FB_STAGE_SCATTERING_DENSITY:
+            if (order < 2) return fail(FB_ERR_INVALID_ARGUMENT, "scattering_density needs order >= 2 (scattering_density.comp:22)");
+            e = fastk ? fast::scattering_density(c, (int)order, r0, r1) : ref::scattering_density(c, (int)order, r0, r1);
+            break;
+        case FB_STAGE_INDIRECT_IRRADIANCE:
+            if (order < 1) return fail(FB_ERR_INVALID_ARGUMENT, "indirect_irradiance needs order >= 1 (indirect_irradiance.comp:18)");
+            e = fastk ? fast::indirect_irradiance(c, (int)order) : ref::indirect_irradiance(c, (int)order);
+            break;
+        case FB_STAGE_MULTIPLE_SCATTERING: e = fastk ? fast::multiple_scattering(c, r0, r1) : ref::multiple_scattering(c, r0, r1); break;
+        case FB_STAGE_CLEAR_IRRADIANCE:
+            e = cudaMemsetAsync(c.img.irradiance, 0, image_bytes(c.P, FB_IMAGE_IRRADIANCE), c.stream);
+            break;
+        default: return fail(FB_ERR_INVALID_ARGUMENT, "unknown stage");
+    }
+    if (fastk && stage <= FB_STAGE_MULTIPLE_SCATTERING) n = fast::launches_per_stage(stage);
+    if (e != cudaSuccess) return cuda_fail(e, "stage launch");
+    if (launches) *launches += n;
+    return FB_OK;
+}
+
+// The recorded command stream, src/precompute.rs:1671-2048.  Stream order replaces the pipeline
+// barriers; the parameter block travels as a kernel argument instead of vkCmdUpdateBuffer.
+static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
+    LaunchCtx c = make_ctx(p, s);
+    const int R = p->P.scattering_r_size;
+    int st;
+#define STAGE(stage, ord) if ((st = run_stage(p, c, stage, ord, 0, R, launches)) != FB_OK) return st
+    STAGE(FB_STAGE_TRANSMITTANCE, 0);          // :1726-1745
+    STAGE(FB_STAGE_DIRECT_IRRADIANCE, 0);      // :1760-1779  -> delta_irradiance
+    STAGE(FB_STAGE_SINGLE_SCATTERING, 0);      // :1781-1800
+    STAGE(FB_STAGE_CLEAR_IRRADIANCE, 0);       // :1802-1831  direct irradiance is not accumulated
+    for (uint32_t order = 2; order <= p->order; ++order) {   // :1853
+        STAGE(FB_STAGE_SCATTERING_DENSITY, order);           // :1878-1904, push constant `order`
+        STAGE(FB_STAGE_INDIRECT_IRRADIANCE, order - 1);      // :1927-1953, push constant `order - 1`
+        STAGE(FB_STAGE_MULTIPLE_SCATTERING, 0);              // :1979-1998
+    }
+#undef STAGE
+    return FB_OK;
+}
+
+int fb_atmosphere_build(FbBuilder* b, const FbParams* params, uint32_t order, void* stream, FbPending** out) {
+    int st = fb_atmosphere_allocate(b, params, order, out);
+    if (st != FB_OK) return st;
+    DeviceGuard g(b->device);
+    int launches = 0;
+    st = enqueue_all(*out, (cudaStream_t)stream, &launches);
+    (*out)->launches = launches;
+    if (st != FB_OK) { fb_pending_destroy(*out); *out = nullptr; }
+    return st;
+}
+
+int fb_pending_resubmit(FbPending* p, void* stream) {
+    if (!p || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_resubmit: NULL / already taken");
+    DeviceGuard g(p->builder->device);
+    if (!p->graph) {
+        cudaStream_t cap;
+        FB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        int launches = 0, st = FB_OK;
+        if (e == cudaSuccess) st = enqueue_all(p, cap, &launches);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e2 = (e == cudaSuccess) ? cudaStreamEndCapture(cap, &graph) : e;
+        cudaStreamDestroy(cap);
+        if (st != FB_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        if (e2 != cudaSuccess) return cuda_fail(e2, "stream capture");
+        e = cudaGraphInstantiate(&p->graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { p->graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+        p->launches = launches;
+    }
+    FB_CUDA(cudaGraphLaunch(p->graph, (cudaStream_t)stream));
+    return FB_OK;
+}
+int fb_pending_launch_count(const FbPending* p) { return p ? p->launches : 0; }
+
+int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_begin, uint32_t r_end, void* stream) {
+    if (!p) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_run_stage: NULL");
+    const uint32_t R = (uint32_t)p->P.scattering_r_size;
+    if (r_end == 0) r_end = R;
+    if (r_begin >= r_end || r_end > R) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_run_stage: bad r slab");
+    DeviceGuard g(p->builder->device);
+    LaunchCtx c = make_ctx(p, (cudaStream_t)stream);
+    return run_stage(p, c, stage, order, (int)r_begin, (int)r_end, nullptr);
+}
+
+int fb_pending_image(FbPending* p, int image, void** dev_ptr, size_t* bytes) {
+    if (!p || image < 0 || image >= FB_IMAGE_COUNT) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_image");
+    if (dev_ptr) *dev_ptr = image_ptr(p, image);
+    if (bytes) *bytes = image_bytes(p->P, image);
+    return FB_OK;
+}
+int fb_pending_upload(FbPending* p, int image, const void* host, size_t bytes, void* stream) {
+    if (!p || !host || image < 0 || image >= FB_IMAGE_COUNT) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_upload");
+    if (bytes != image_bytes(p->P, image)) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_upload: size mismatch");
+    DeviceGuard g(p->builder->device);
+    FB_CUDA(cudaMemcpyAsync(image_ptr(p, image), host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return FB_OK;
+}
+int fb_pending_download(FbPending* p, int image, void* host, size_t bytes, void* stream) {
+    if (!p || !host || image < 0 || image >= FB_IMAGE_COUNT) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_download");
+    if (bytes != image_bytes(p->P, image)) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_download: size mismatch");
+    DeviceGuard g(p->builder->device);
+    FB_CUDA(cudaMemcpyAsync(host, image_ptr(p, image), bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return FB_OK;
+}
+
+int fb_pending_atmosphere(FbPending* p, const FbAtmosphere** out) {
+    if (!p || !out || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_atmosphere");
+    *out = p->inner;
+    return FB_OK;
+}
+int fb_pending_assert_ready(FbPending* p, int check, FbAtmosphere** out) {
+    if (!p || !out || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_assert_ready");
+    DeviceGuard g(p->builder->device);
+    if (check) {
+        // cudaFree below synchronises the device anyway; the check only turns a too-early call
+        // (which in the reference is undefined behaviour) into an error code.
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+    }
+    *out = p->inner;
+    p->inner = nullptr;
+    fb_pending_destroy(p);
+    return FB_OK;
+}
+
+int fb_atmosphere_transmittance(const FbAtmosphere* a, const void** ptr, FbExtent2D* e) {
+    if (!a) return fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+    if (ptr) *ptr = a->transmittance;
+    if (e) fb_params_transmittance_extent(&a->P, e);
+    return FB_OK;
+}
+int fb_atmosphere_scattering(const FbAtmosphere* a, const void** ptr, FbExtent3D* e) {
+    if (!a) return fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+    if (ptr) *ptr = a->scattering;
+    if (e) fb_params_scattering_extent(&a->P, e);
+    return FB_OK;
+}
+int fb_atmosphere_irradiance(const FbAtmosphere* a, const void** ptr, FbExtent2D* e) {
+    if (!a) return fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+    if (ptr) *ptr = a->irradiance;
+    if (e) fb_params_irradiance_extent(&a->P, e);
+    return FB_OK;
+}
+int fb_atmosphere_params(const FbAtmosphere* a, FbParams* out) {
+    if (!a || !out) return fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+    *out = a->P;
+    return FB_OK;
+}
+static int read_back(const FbAtmosphere* a, const void* src, size_t want, void* host, size_t bytes, void* stream) {
+    if (!a || !host) return fail(FB_ERR_INVALID_ARGUMENT, "read: NULL");
+    if (bytes != want) return fail(FB_ERR_INVALID_ARGUMENT, "read: size mismatch");
+    DeviceGuard g(a->device);
+    FB_CUDA(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return FB_OK;
+}
+int fb_atmosphere_read_transmittance(const FbAtmosphere* a, void* host, size_t bytes, void* stream) {
+    return a ? read_back(a, a->transmittance, image_bytes(a->P, FB_IMAGE_TRANSMITTANCE), host, bytes, stream)
+             : fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+}
+int fb_atmosphere_read_scattering(const FbAtmosphere* a, void* host, size_t bytes, void* stream) {
+    return a ? read_back(a, a->scattering, image_bytes(a->P, FB_IMAGE_SCATTERING), host, bytes, stream)
+             : fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+}
+int fb_atmosphere_read_irradiance(const FbAtmosphere* a, void* host, size_t bytes, void* stream) {
+    return a ? read_back(a, a->irradiance, image_bytes(a->P, FB_IMAGE_IRRADIANCE), host, bytes, stream)
+             : fail(FB_ERR_INVALID_ARGUMENT, "atmosphere: NULL");
+}
+
+int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, void* T, void* S, void* E) {
+    if (!b) return fail(FB_ERR_INVALID_ARGUMENT, "fb_precompute_host: NULL builder");
+    DeviceGuard g(b->device);
+    cudaStream_t s;
+    FB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    FbPending* pend = nullptr;
+    int st = fb_atmosphere_build(b, p, order, s, &pend);
+    if (st == FB_OK) {
+        const FbAtmosphere* a = pend->inner;
+        if (T && st == FB_OK) st = fb_atmosphere_read_transmittance(a, T, image_bytes(a->P, FB_IMAGE_TRANSMITTANCE), s);
+        if (S && st == FB_OK) st = fb_atmosphere_read_scattering(a, S, image_bytes(a->P, FB_IMAGE_SCATTERING), s);
+        if (E && st == FB_OK) st = fb_atmosphere_read_irradiance(a, E, image_bytes(a->P, FB_IMAGE_IRRADIANCE), s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (st == FB_OK && e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize");
+        fb_pending_destroy(pend);
+    }
+    cudaStreamDestroy(s);
+    return st;
+}
+
+int fb_atmosphere_build_batch(FbBuilder* b, const FbParams* params, uint32_t n, uint32_t order, void* stream, FbPending** out) {
+    if (!b || !params || !out) return fail(FB_ERR_INVALID_ARGUMENT, "fb_atmosphere_build_batch: NULL");
+    DeviceGuard g(b->device);
+    for (uint32_t i = 0; i < n; ++i) out[i] = nullptr;
+    int st = FB_OK;
+    for (uint32_t i = 0; i < n && st == FB_OK; ++i) st = fb_atmosphere_allocate(b, params + i, order, out + i);
+    // independent atmospheres overlap on side streams that fork from and join into `stream`
+    const uint32_t lanes = n < 8 ? n : 8;
+    std::vector<cudaStream_t> side(lanes, nullptr);
+    cudaEvent_t fork = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (st == FB_OK && lanes) {
+        e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(fork, (cudaStream_t)stream);
+        for (uint32_t l = 0; l < lanes && e == cudaSuccess; ++l) {
+            e = cudaStreamCreateWithFlags(&side[l], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(side[l], fork, 0);
+        }
+        for (uint32_t i = 0; i < n && e == cudaSuccess && st == FB_OK; ++i) {
+            int launches = 0;
+            st = enqueue_all(out[i], side[i % lanes], &launches);
+            out[i]->launches = launches;
+        }
+        for (uint32_t l = 0; l < lanes && e == cudaSuccess; ++l) {
+            cudaEvent_t join;
+            e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(join, side[l]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)stream, join, 0);
+            cudaEventDestroy(join);
+        }
+    }
+    for (uint32_t l = 0; l < lanes; ++l) if (side[l]) cudaStreamDestroy(side[l]);   // deferred until the work drains
+    if (fork) cudaEventDestroy(fork);
+    if (e != cudaSuccess && st == FB_OK) st = cuda_fail(e, "batch stream fork/join");
+    if (st != FB_OK)
+        for (uint32_t i = 0; i < n; ++i) { fb_pending_destroy(out[i]); out[i] = nullptr; }
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// renderer
+// ---------------------------------------------------------------------------------------------
+int fb_renderer_create(FbBuilder* b, FbRenderer** out) {
+    if (!b || !out) return fail(FB_ERR_INVALID_ARGUMENT, "fb_renderer_create: NULL");
+    FbRenderer* r = new (std::nothrow) FbRenderer();
+    if (!r) return fail(FB_ERR_OUT_OF_MEMORY, "host allocation");
+    r->device = b->device;
+    r->kernels = b->kernels;
+    r->sweep_draws = nullptr;
+    r->sweep_capacity = 0;
+    *out = r;
+    return FB_OK;
+}
+void fb_renderer_destroy(FbRenderer* r) {
+    if (!r) return;
+    DeviceGuard g(r->device);
+    cudaFree(r->sweep_draws);
+    delete r;
+}
+
+static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, uint32_t views, const float* depth,
+                       float* color, float* transm, float* blend, uint32_t w, uint32_t h, void* stream) {
+    if (!r || !a || !d || !depth) return fail(FB_ERR_INVALID_ARGUMENT, "draw: NULL argument");
+    if (r->device != a->device) return fail(FB_ERR_INVALID_ARGUMENT, "draw: renderer and atmosphere live on different devices");
+    if (h > 65535 || views > 65535) return fail(FB_ERR_INVALID_ARGUMENT, "draw: height / views exceed the launch grid");
+    DeviceGuard g(r->device);
+    const FbDrawParams* dev = nullptr;
+    if (views > 1) {
+        if (views > r->sweep_capacity) {
+            cudaFree(r->sweep_draws);
+            r->sweep_draws = nullptr;
+            r->sweep_capacity = 0;
+            FB_CUDA(cudaMalloc((void**)&r->sweep_draws, (size_t)views * sizeof(FbDrawParams)));
+            r->sweep_capacity = views;
+        }
+        FB_CUDA(cudaMemcpyAsync(r->sweep_draws, d, (size_t)views * sizeof(FbDrawParams), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        dev = r->sweep_draws;
+    }
+    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, d[0], dev, views, depth, (float4*)color, (float4*)transm,
+                               (float4*)blend, w, h, r->kernels, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "render_sky launch");
+    return FB_OK;
+}
+
+int fb_renderer_draw(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, const float* depth, float* color,
+                     float* transm, uint32_t w, uint32_t h, void* stream) {
+    return draw_common(r, a, d, 1, depth, color, transm, nullptr, w, h, stream);
+}
+int fb_renderer_draw_blend(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, const float* depth, float* fbuf,
+                           uint32_t w, uint32_t h, void* stream) {
+    if (!fbuf) return fail(FB_ERR_INVALID_ARGUMENT, "draw_blend: NULL framebuffer");
+    return draw_common(r, a, d, 1, depth, nullptr, nullptr, fbuf, w, h, stream);
+}
+int fb_renderer_draw_sweep(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, uint32_t views, const float* depth,
+                           float* color, float* transm, uint32_t w, uint32_t h, void* stream) {
+    if (views == 0) return FB_OK;
+    return draw_common(r, a, d, views, depth, color, transm, nullptr, w, h, stream);
+}
+int fb_renderer_draw_host(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, const float* depth_host, float* color_host,
+                          float* transm_host, uint32_t w, uint32_t h) {
+    if (!r || !a || !d || !depth_host) return fail(FB_ERR_INVALID_ARGUMENT, "draw_host: NULL argument");
+    DeviceGuard g(r->device);
+    const size_t npx = (size_t)w * h;
+    float *depth = nullptr, *color = nullptr, *transm = nullptr;
+    cudaStream_t s = nullptr;
+    int st = FB_OK;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&depth, npx * sizeof(float));
+    if (e == cudaSuccess && color_host) e = cudaMalloc((void**)&color, npx * sizeof(float4));
+    if (e == cudaSuccess && transm_host) e = cudaMalloc((void**)&transm, npx * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(depth, depth_host, npx * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) st = fb_renderer_draw(r, a, d, depth, color, transm, w, h, s);
+    if (e == cudaSuccess && st == FB_OK && color_host) e = cudaMemcpyAsync(color_host, color, npx * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && st == FB_OK && transm_host) e = cudaMemcpyAsync(transm_host, transm, npx * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(depth); cudaFree(color); cudaFree(transm);
+    if (s) cudaStreamDestroy(s);
+    if (e != cudaSuccess) return cuda_fail(e, "draw_host");
+    return st;
+}
+
+int fb_sky_radiance(const FbAtmosphere* a, const float* camera, const float* view_ray, const float* sun_direction, uint64_t n,
+                    float* radiance_out, float* transmittance_out, void* stream) {
+    if (!a || !camera || !view_ray || !sun_direction || !radiance_out || !transmittance_out)
+        return fail(FB_ERR_INVALID_ARGUMENT, "fb_sky_radiance: NULL argument");
+    DeviceGuard g(a->device);
+    cudaError_t e = sky_radiance(a->P, a->transmittance, a->scattering, camera, view_ray, sun_direction, n, radiance_out,
+                                 transmittance_out, (cudaStream_t)stream);
+    return e == cudaSuccess ? FB_OK : cuda_fail(e, "sky_radiance launch");
+}
+int fb_sun_and_sky_irradiance(const FbAtmosphere* a, const float* point, const float* normal, const float* sun_direction,
+                              uint64_t n, float* sun_out, float* sky_out, void* stream) {
+    if (!a || !point || !normal || !sun_direction || !sun_out || !sky_out)
+        return fail(FB_ERR_INVALID_ARGUMENT, "fb_sun_and_sky_irradiance: NULL argument");
+    DeviceGuard g(a->device);
+    cudaError_t e = sun_sky_irradiance(a->P, a->transmittance, a->irradiance, point, normal, sun_direction, n, sun_out, sky_out,
+                                       (cudaStream_t)stream);
+    return e == cudaSuccess ? FB_OK : cuda_fail(e, "sun_sky_irradiance launch");
+}

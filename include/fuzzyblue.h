@@ -1,0 +1,241 @@
+/* fuzzyblue.h — C ABI of the B200-native atmosphere LUT precompute + sky evaluation.
+ *
+ * This is the drop-in boundary for the one hot path of Ralith/fuzzyblue: what a Rust shim
+ * crate (rust/src/lib.rs), the C++ mirror (include/fuzzyblue.hpp) and the
+ * Python ctypes mirror (fuzzyblue_b200/api.py) bind.  Plain pointers and sizes only; no torch,
+ * no Vulkan types.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout, file:line).
+ *
+ * Execution model: the reference only *records* into a caller-owned VkCommandBuffer
+ * (src/precompute.rs:1077-1081, :2108-2110); here every `stream` argument is a caller-owned
+ * cudaStream_t (passed as void*; NULL = the legacy default stream) and the call enqueues work on
+ * it and returns without waiting.  Completion is the caller's business, exactly as
+ * vkQueueSubmit + fence is in the reference (tests/smoke.rs:147-155).
+ *
+ * Errors: the reference panics through .unwrap(); this ABI returns an FbStatus and never
+ * aborts.  fb_last_error() gives a thread-local message for the last non-OK status.
+ *
+ * LUT memory (read-back layout of examples/dump.rs:175-193, x fastest, tightly packed):
+ *   transmittance  [T_r][T_mu][4]                 float32  (R32G32B32A32_SFLOAT, precompute.rs:1170)
+ *   irradiance     [E_r][E_mu_s][4]               float32  (precompute.rs:1191)
+ *   scattering     [S_r][S_mu][S_nu*S_mu_s][4]    float16  (R16G16B16A16_SFLOAT, precompute.rs:1215)
+ */
+#ifndef FUZZYBLUE_H_
+#define FUZZYBLUE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FB_API __attribute__((visibility("default")))
+#else
+#define FB_API
+#endif
+
+typedef enum FbStatus {
+    FB_OK = 0,
+    FB_ERR_INVALID_ARGUMENT = 1, /* NULL handle, bad dims (nu_size < 2, odd mu_size, ...), bad slab */
+    FB_ERR_CUDA = 2,             /* a CUDA runtime call failed; see fb_last_error() */
+    FB_ERR_OUT_OF_MEMORY = 3,
+    FB_ERR_NO_DEVICE = 4,        /* no CUDA device / not an sm_100 part: there is NO CPU fallback */
+    FB_ERR_NOT_READY = 5         /* fb_pending_assert_ready() while the stream is still running */
+} FbStatus;
+
+/* ---- the atmosphere parameter block: shaders/params.h:9-87, host mirror ParamsRaw
+ *      src/precompute.rs:937-1033.  Byte-identical std140 layout, 320 bytes. ------------------- */
+typedef struct FbDensityProfileLayer { /* params.h:9-15; 32-byte stride (precompute.rs:1012-1021) */
+    float width, exp_term, exp_scale, linear_term, constant_term;
+    float _pad[3];
+} FbDensityProfileLayer;
+
+typedef struct FbDensityProfile { /* params.h:21-23 */
+    FbDensityProfileLayer layers[2];
+} FbDensityProfile;
+
+typedef struct FbParams {
+    float solar_irradiance[3];      /*   0 */
+    float sun_angular_radius;       /*  12 */
+    float rayleigh_scattering[3];   /*  16 */
+    float bottom_radius;            /*  28  km */
+    float mie_scattering[3];        /*  32 */
+    float top_radius;               /*  44  km */
+    float mie_extinction[3];        /*  48 */
+    float mie_phase_function_g;     /*  60 */
+    float ground_albedo[3];         /*  64 */
+    float mu_s_min;                 /*  76 */
+    float absorption_extinction[3]; /*  80  (host field is spelled `absorbtion_extinction`) */
+    int32_t transmittance_mu_size;  /*  92 */
+    int32_t transmittance_r_size;   /*  96 */
+    int32_t scattering_r_size;      /* 100 */
+    int32_t scattering_mu_size;     /* 104 */
+    int32_t scattering_mu_s_size;   /* 108 */
+    int32_t scattering_nu_size;     /* 112 */
+    int32_t irradiance_mu_s_size;   /* 116 */
+    int32_t irradiance_r_size;      /* 120 */
+    int32_t _pad;                   /* 124 */
+    FbDensityProfile rayleigh_density;   /* 128 */
+    FbDensityProfile mie_density;        /* 192 */
+    FbDensityProfile absorption_density; /* 256 */
+} FbParams;                              /* 320 */
+
+/* DrawParamsRaw, src/render.rs:254-271 == push constants of shaders/render_sky.frag:16-20. 92 bytes. */
+typedef struct FbDrawParams {
+    float inverse_viewproj[4][4]; /* [column][row]: (projection * view)^-1, world units metres */
+    float camera_position[3];     /* km, planet frame */
+    uint32_t _pad;
+    float sun_direction[3];
+} FbDrawParams;
+
+typedef struct FbExtent2D { uint32_t width, height; } FbExtent2D;
+typedef struct FbExtent3D { uint32_t width, height, depth; } FbExtent3D;
+
+typedef struct FbBuilder FbBuilder;       /* Builder            src/precompute.rs:32-58  */
+typedef struct FbPending FbPending;       /* PendingAtmosphere  src/precompute.rs:2111-2120 */
+typedef struct FbAtmosphere FbAtmosphere; /* Atmosphere         src/precompute.rs:1036-1043 */
+typedef struct FbRenderer FbRenderer;     /* Renderer           src/render.rs:13-19 */
+
+/* Images an in-flight precompute owns (descriptor map src/precompute.rs:1259-1601). */
+typedef enum FbImage {
+    FB_IMAGE_TRANSMITTANCE = 0,             /* f32x4 2-D, kept   */
+    FB_IMAGE_IRRADIANCE = 1,                /* f32x4 2-D, kept   */
+    FB_IMAGE_SCATTERING = 2,                /* f16x4 3-D, kept   */
+    FB_IMAGE_DELTA_IRRADIANCE = 3,          /* f32x4 2-D, temp   */
+    FB_IMAGE_DELTA_RAYLEIGH = 4,            /* f16x4 3-D, temp   */
+    FB_IMAGE_DELTA_MIE = 5,                 /* f16x4 3-D, temp   */
+    FB_IMAGE_SCATTERING_DENSITY = 6,        /* f16x4 3-D, temp   */
+    FB_IMAGE_DELTA_MULTIPLE_SCATTERING = 7, /* f16x4 3-D, temp   */
+    FB_IMAGE_COUNT = 8
+} FbImage;
+
+/* The six compute shaders (shaders/*.comp) as individually launchable stages. */
+typedef enum FbStage {
+    FB_STAGE_TRANSMITTANCE = 0,       /* transmittance.comp:71-80 */
+    FB_STAGE_DIRECT_IRRADIANCE = 1,   /* direct_irradiance.comp:36-46 */
+    FB_STAGE_SINGLE_SCATTERING = 2,   /* single_scattering.comp:89-101 */
+    FB_STAGE_SCATTERING_DENSITY = 3,  /* scattering_density.comp:144-155, push constant = order */
+    FB_STAGE_INDIRECT_IRRADIANCE = 4, /* indirect_irradiance.comp:59-74, push constant = order */
+    FB_STAGE_MULTIPLE_SCATTERING = 5, /* multiple_scattering.comp:81-93 */
+    FB_STAGE_CLEAR_IRRADIANCE = 6     /* vkCmdClearColorImage, precompute.rs:1802-1831 */
+} FbStage;
+
+/* Kernel families.  Both follow the same shaders and produce the same tables within the parity
+ * tolerance; FAST is the product, REFERENCE the one-thread-per-texel, contraction-free
+ * transcription kept as the on-device cross-check. */
+typedef enum FbKernels { FB_KERNELS_FAST = 0, FB_KERNELS_REFERENCE = 1 } FbKernels;
+
+FB_API const char* fb_status_string(int status);
+FB_API const char* fb_last_error(void);
+FB_API const char* fb_version(void);
+
+/* Parameters::default(), src/precompute.rs:849-935 (Earth).  `order` is not part of the uniform
+ * block in the reference either (Parameters.order, :700); its default is 4. */
+FB_API int fb_params_default(FbParams* out);
+FB_API uint32_t fb_params_default_order(void);
+/* Parameters::{transmittance,irradiance,scattering}_extent(), src/precompute.rs:771-793 */
+FB_API int fb_params_transmittance_extent(const FbParams* p, FbExtent2D* out);
+FB_API int fb_params_irradiance_extent(const FbParams* p, FbExtent2D* out);
+FB_API int fb_params_scattering_extent(const FbParams* p, FbExtent3D* out);
+/* FB_OK when the dims are usable (every size >= 2, scattering_mu_size even, products fit int32). */
+FB_API int fb_params_validate(const FbParams* p);
+
+/* Builder::new, src/precompute.rs:61-68: one-time, device-wide setup.  `device` is a CUDA ordinal. */
+FB_API int fb_builder_create(int device, FbBuilder** out);
+FB_API void fb_builder_destroy(FbBuilder* b);
+FB_API int fb_builder_set_kernels(FbBuilder* b, int kernels /* FbKernels */);
+FB_API int fb_builder_device(const FbBuilder* b);
+FB_API int fb_builder_sm_count(const FbBuilder* b);
+
+/* Atmosphere::build, src/precompute.rs:1077-2073: allocate the 3 kept + 5 temporary images and
+ * enqueue the whole command stream of :1671-2048 on `stream`. */
+FB_API int fb_atmosphere_build(FbBuilder* b, const FbParams* p, uint32_t order, void* stream, FbPending** out);
+/* Same allocation, nothing enqueued: the caller drives stages itself (tests, r-slab sharding). */
+FB_API int fb_atmosphere_allocate(FbBuilder* b, const FbParams* p, uint32_t order, FbPending** out);
+/* Re-enqueue the identical command stream on the images `p` already owns — the analogue of
+ * re-submitting the pre-recorded command buffer, which is what benches/precompute.rs:138-148
+ * times.  The stream is replayed from a CUDA graph instantiated on first use. */
+FB_API int fb_pending_resubmit(FbPending* p, void* stream);
+/* Number of kernel launches / memset nodes one submit performs (for launch accounting). */
+FB_API int fb_pending_launch_count(const FbPending* p);
+
+/* One stage on the slab r in [r_begin, r_end) of the scattering r axis (3-D stages) or on the whole
+ * table (2-D stages; slab ignored).  r_end = 0 means "to the end".  `order` is the push constant
+ * the reference passes for that stage (precompute.rs:1897, :1946); ignored elsewhere. */
+FB_API int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_begin, uint32_t r_end, void* stream);
+/* Device pointer + byte size of one image (linear layout above), for collectives and interop. */
+FB_API int fb_pending_image(FbPending* p, int image, void** dev_ptr, size_t* bytes);
+/* Host <-> image copies (async on `stream`; `bytes` must equal the image size). */
+FB_API int fb_pending_upload(FbPending* p, int image, const void* host, size_t bytes, void* stream);
+FB_API int fb_pending_download(FbPending* p, int image, void* host, size_t bytes, void* stream);
+
+/* PendingAtmosphere::atmosphere, :2203-2206 — borrowed, valid while `p` lives. */
+FB_API int fb_pending_atmosphere(FbPending* p, const FbAtmosphere** out);
+/* PendingAtmosphere::assert_ready, :2208-2211 — consumes `p`, frees the five temporaries.  The
+ * caller asserts the stream has finished; pass check=1 to have it verified (FB_ERR_NOT_READY). */
+FB_API int fb_pending_assert_ready(FbPending* p, int check, FbAtmosphere** out);
+/* Drop for PendingAtmosphere, :2122-2140 (also drops the atmosphere if it was never taken). */
+FB_API void fb_pending_destroy(FbPending* p);
+
+/* Atmosphere::{transmittance,scattering,irradiance}{,_extent}, :2075-2101.  Device pointers to the
+ * linear tables described at the top of this header. */
+FB_API int fb_atmosphere_transmittance(const FbAtmosphere* a, const void** dev_ptr, FbExtent2D* extent);
+FB_API int fb_atmosphere_scattering(const FbAtmosphere* a, const void** dev_ptr, FbExtent3D* extent);
+FB_API int fb_atmosphere_irradiance(const FbAtmosphere* a, const void** dev_ptr, FbExtent2D* extent);
+FB_API int fb_atmosphere_params(const FbAtmosphere* a, FbParams* out);
+/* examples/dump.rs:110-193: tightly packed read-back into host memory (async on `stream`). */
+FB_API int fb_atmosphere_read_transmittance(const FbAtmosphere* a, void* host, size_t bytes, void* stream);
+FB_API int fb_atmosphere_read_scattering(const FbAtmosphere* a, void* host, size_t bytes, void* stream);
+FB_API int fb_atmosphere_read_irradiance(const FbAtmosphere* a, void* host, size_t bytes, void* stream);
+/* Drop for Atmosphere, :1045-1073 */
+FB_API void fb_atmosphere_destroy(FbAtmosphere* a);
+
+/* Host-buffer convenience = what a caller of the reference does end to end (build, submit, wait,
+ * read back as examples/dump.rs does): params in host memory, three tables out to host memory.
+ * Any output pointer may be NULL.  Synchronous. */
+FB_API int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, void* transmittance_f32,
+                              void* scattering_f16, void* irradiance_f32);
+
+/* Renderer::new, src/render.rs:34-40 (render pass / subpass / frame count have no CUDA meaning). */
+FB_API int fb_renderer_create(FbBuilder* b, FbRenderer** out);
+FB_API void fb_renderer_destroy(FbRenderer* r);
+/* Renderer::draw, src/render.rs:209-236 + shaders/render_sky.frag:24-35, one thread per pixel.
+ *   depth        [h][w] float32 device pointer — the input attachment (render_sky.frag:22)
+ *   color_out    [h][w][4] float32: (radiance.rgb, 0)        (location 0, index 0)
+ *   transm_out   [h][w][4] float32: (transmittance.rgb, 1)   (location 0, index 1)
+ * Either output may be NULL. */
+FB_API int fb_renderer_draw(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, const float* depth,
+                            float* color_out, float* transm_out, uint32_t width, uint32_t height, void* stream);
+/* The fixed-function dual-source blend of src/render.rs:124-137 applied to a caller framebuffer:
+ * dst.rgb = color.rgb + dst.rgb * transmittance.rgb, dst.a kept. */
+FB_API int fb_renderer_draw_blend(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, const float* depth,
+                                  float* framebuffer_rgba, uint32_t width, uint32_t height, void* stream);
+/* A sweep of `views` draws over one depth buffer per view ([views][h][w]); outputs [views][h][w][4]. */
+FB_API int fb_renderer_draw_sweep(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, uint32_t views,
+                                  const float* depth, float* color_out, float* transm_out, uint32_t width,
+                                  uint32_t height, void* stream);
+/* Host-buffer variant (pageable or pinned host pointers; copies inside; synchronous). */
+FB_API int fb_renderer_draw_host(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams* d, const float* depth_host,
+                                 float* color_host, float* transm_host, uint32_t width, uint32_t height);
+
+/* Shader-library functions downstream engines include (no in-tree entry point in the reference):
+ * GetSkyRadiance, shaders/render_sky.h:45-109, and GetSunAndSkyIrradiance,
+ * shaders/render_lighting.h:10-28, evaluated for n independent queries.  All pointers are device
+ * pointers to [n][3] float32 arrays. */
+FB_API int fb_sky_radiance(const FbAtmosphere* a, const float* camera, const float* view_ray, const float* sun_direction,
+                           uint64_t n, float* radiance_out, float* transmittance_out, void* stream);
+FB_API int fb_sun_and_sky_irradiance(const FbAtmosphere* a, const float* point, const float* normal,
+                                     const float* sun_direction, uint64_t n, float* sun_irradiance_out,
+                                     float* sky_irradiance_out, void* stream);
+
+/* Batch of independent atmospheres (BASELINE.json config 4): `n` parameter blocks, one precompute
+ * each, round-robin over an internal pool of streams that all fork from / join into `stream`. */
+FB_API int fb_atmosphere_build_batch(FbBuilder* b, const FbParams* params, uint32_t n, uint32_t order, void* stream,
+                                     FbPending** out /* [n] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUZZYBLUE_H_ */
