@@ -1,0 +1,115 @@
+"""GPU parity of the sky evaluation (shaders/render_sky.frag) and the two shader-library queries, through the C ABI.
+
+Tolerance: 1e-3 relative on the rendered radiance and transmittance per pixel, with an absolute floor of 1e-3 of the
+frame's peak radiance for the colour output: geometry pixels compute `scattering - T * scattering_p`
+(render_sky.h:178), a difference of two nearly equal table look-ups whose relative error is unbounded by construction.
+"""
+import numpy as np
+import pytest
+
+import fuzzyblue_b200 as fb
+from fuzzyblue_b200 import api, synthetic
+from oracle import oracle as O
+
+from .conftest import DUMP_DIMS
+
+pytestmark = pytest.mark.gpu
+W, H = 96, 54
+
+
+@pytest.fixture(scope="module", params=["fast", "reference"])
+def scene(request):
+    import torch
+    kernels = api.KERNELS_FAST if request.param == "fast" else api.KERNELS_REFERENCE
+    builder = fb.Builder(0, kernels=kernels)
+    p = fb.Parameters(**DUMP_DIMS)
+    pend = fb.Atmosphere.build(builder, None, p)
+    torch.cuda.synchronize()
+    atm = pend.assert_ready()
+    T = atm.read_transmittance().astype(np.float64)
+    S = atm.read_scattering().astype(np.float64)
+    E = atm.read_irradiance().astype(np.float64)
+    draws, extra = synthetic.camera_sweep(24, W, H)
+    depths = [synthetic.analytic_depth(inv, eye, W, H) for inv, eye in extra]
+    return dict(builder=builder, atm=atm, T=T, S=S, E=E, draws=draws, depths=depths, op=O.Params(**DUMP_DIMS),
+                renderer=fb.Renderer(builder))
+
+
+def oracle_draw(scene, k):
+    d = scene["draws"][k]
+    return O.render(scene["op"], O.F32, scene["T"], scene["S"], O.pack_draw(d.inverse_viewproj, d.camera_position, d.sun_direction),
+                    scene["depths"][k])
+
+
+def close(got, want, floor):
+    return np.abs(got.astype(np.float64) - want) <= 1e-3 * np.maximum(np.abs(want), floor)
+
+
+def test_draw_matches_oracle_over_the_sweep(scene):
+    n_ground = n_space = 0
+    for k in range(len(scene["draws"])):
+        color, transm = scene["renderer"].draw_host(scene["atm"], scene["draws"][k], scene["depths"][k])
+        oc, ot = oracle_draw(scene, k)
+        assert np.all(np.isfinite(color)) and np.all(np.isfinite(transm))
+        floor = 1e-3 * max(float(np.abs(oc).max()), 1e-9)
+        okc, okt = close(color, oc, floor), close(transm, ot, 1e-6)
+        assert okc.all(), (k, float(np.abs(color - oc).max()), floor)
+        assert okt.all(), (k, float(np.abs(transm - ot).max()))
+        assert np.all(color[..., 3] == 0) and np.all(transm[..., 3] == 1)
+        n_ground += int((scene["depths"][k] > 0).sum())
+        n_space += scene["draws"][k].camera_position[2] > 6420.0
+    assert n_ground > 1000 and n_space >= 2      # both branches of render_sky.h:127-136 and :154 were exercised
+
+
+def test_sweep_equals_individual_draws_and_blend(scene):
+    import torch
+    n = 6
+    depth = torch.from_numpy(np.stack(scene["depths"][:n])).cuda()
+    color = torch.empty((n, H, W, 4), device="cuda")
+    transm = torch.empty((n, H, W, 4), device="cuda")
+    r = scene["renderer"]
+    r.draw_sweep(None, scene["atm"], scene["draws"][:n], depth, color, transm, W, H)
+    torch.cuda.synchronize()
+    for k in range(n):
+        c1, t1 = r.draw_host(scene["atm"], scene["draws"][k], scene["depths"][k])
+        assert np.array_equal(color[k].cpu().numpy(), c1) and np.array_equal(transm[k].cpu().numpy(), t1)
+    # fixed-function blend of src/render.rs:124-137: dst.rgb = color + dst.rgb * transmittance, alpha kept
+    fbuf = torch.rand((H, W, 4), device="cuda")
+    before = fbuf.clone()
+    r.set_depth_buffer(0, depth[3])
+    r.draw_blend(None, scene["atm"], 0, scene["draws"][3], fbuf, W, H)
+    torch.cuda.synchronize()
+    want = color[3, ..., :3] + before[..., :3] * transm[3, ..., :3]
+    assert torch.allclose(fbuf[..., :3], want, rtol=1e-6, atol=1e-7)
+    assert torch.equal(fbuf[..., 3], before[..., 3])
+
+
+def test_library_queries(scene):
+    """GetSkyRadiance (render_sky.h:45-109) and GetSunAndSkyIrradiance (render_lighting.h:10-28)."""
+    import torch
+    rng = np.random.default_rng(7)
+    n = 4096
+    alt = np.exp(rng.uniform(np.log(1e-3), np.log(500.0), n))
+    cam = np.stack([np.zeros(n), np.zeros(n), 6360.0 + alt], 1)
+    def unit(v):
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    view, sun, nrm = unit(rng.normal(size=(n, 3))), unit(rng.normal(size=(n, 3))), unit(rng.normal(size=(n, 3)))
+    f32 = lambda a: torch.from_numpy(a.astype(np.float32)).cuda()
+    dcam, dview, dsun, dn = f32(cam), f32(view), f32(sun), f32(nrm)
+    rad, tr = torch.empty((n, 3), device="cuda"), torch.empty((n, 3), device="cuda")
+    fb.sky_radiance(scene["atm"], dcam, dview, dsun, n, rad, tr)
+    orad, otr = O.sky_radiance(scene["op"], O.F32, scene["T"], scene["S"], cam.astype(np.float32), view.astype(np.float32),
+                               sun.astype(np.float32))
+    torch.cuda.synchronize()
+    assert close(rad.cpu().numpy(), orad, 1e-3 * np.abs(orad).max()).all()
+    assert close(tr.cpu().numpy(), otr, 1e-6).all()
+    pts = cam.copy()
+    pts[:, 2] = np.minimum(pts[:, 2], 6419.0)
+    dp = f32(pts)
+    direct, sky = torch.empty((n, 3), device="cuda"), torch.empty((n, 3), device="cuda")
+    fb.sun_and_sky_irradiance(scene["atm"], dp, dn, dsun, n, direct, sky)
+    od, osk = O.sun_sky_irradiance(scene["op"], O.F32, scene["T"], scene["E"], pts.astype(np.float32), nrm.astype(np.float32),
+                                   sun.astype(np.float32))
+    torch.cuda.synchronize()
+    assert close(direct.cpu().numpy(), od, 1e-6).all()
+    assert close(sky.cpu().numpy(), osk, 1e-9).all()
