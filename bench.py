@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the hot path (BASELINE.json): LUT precompute ms at default dims, 4 orders.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full Atmosphere::build command stream (transmittance, direct irradiance, single scattering and three
+density / indirect-irradiance / multiple-scattering passes) replayed from the pre-recorded CUDA graph on pre-allocated
+images — what /root/reference/benches/precompute.rs:138-148 times (queue_submit of a pre-recorded command buffer +
+device_wait_idle), at the default dims of BASELINE.json configs[1] instead of the bench's reduced ones.
+At N > 1 every rank builds its own atmosphere per step (independent atmospheres shard with no data-path collective,
+SURVEY.md §8e) and `value` is the time per atmosphere over the whole job: weak scaling.
+
+Prints ONE JSON line (rank 0).  Extra objects: `roofline` (dominant kernel: scattering_density), `cpu_baseline`
+(the CPU oracle port, bounded sample), `render` (the second half of BASELINE.json's metric: sky evaluation Mpixel/s at
+3840x2160), `e2e` (host-buffer path through the C ABI), `clocks`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LUT precompute ms (4 orders, default dims)"
+UNIT = "ms"
+WORKLOAD = "default Earth atmosphere, T 256x64, S 32x128x32x8, E 64x16, 4 orders (BASELINE.json configs[1])"
+
+# Algorithmic work of the dominant kernel, SURVEY.md §8(d): quadrature samples per launch and the per-sample fp32
+# flop tallies (as written in scattering_density.comp vs with every loop-invariant hoisted).
+DENSITY_SAMPLES = 32 * 128 * 256 * 512
+FLOP_AS_WRITTEN = {2: 223.0, 3: 184.0}
+FLOP_HOISTED = {2: 92.0, 3: 63.0}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # the median over samples taken while kernels were in flight: drop idle-clock samples below half of max
+        busy = [c for c in sm if mx and c >= 0.5 * mx[0]] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (fp32 mode = the shaders as written) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_precompute_ms(stride: int):
+    """Estimated full default-dims 4-order precompute on the CPU oracle from a bounded sample: the 2-D stages in full,
+    every 3-D stage on every `stride`-th texel (seeded offset), scaled by `stride`."""
+    import numpy as np
+    from oracle import oracle as O
+    p = O.Params()
+    n_tex = int(np.prod(p.s_shape[:3]))
+    idx = np.arange(stride // 2, n_tex, stride, dtype=np.int64)
+    t = {}
+
+    def timed(name, fn):
+        t0 = time.perf_counter()
+        out = fn()
+        t[name] = time.perf_counter() - t0
+        return out
+
+    T = timed("transmittance", lambda: O.transmittance(p, O.F32))
+    dE = timed("direct_irradiance", lambda: O.direct_irradiance(p, O.F32, T))
+    timed("single_scattering", lambda: O.single_scattering(p, O.F32, T, idx))
+    # the 3-D inputs of the later stages only steer values, not the amount of work: smooth synthetic tables
+    flat = np.full(p.s_shape, 1e-2)
+    timed("density_o2", lambda: O.scattering_density(p, O.F32, 2, T, flat, flat, flat, dE, idx))
+    timed("density_o3", lambda: O.scattering_density(p, O.F32, 3, T, flat, flat, flat, dE, idx))
+    timed("indirect_o1", lambda: O.indirect_irradiance(p, O.F32, 1, flat, flat, flat, np.zeros(p.e_shape)))
+    timed("indirect_o2", lambda: O.indirect_irradiance(p, O.F32, 2, flat, flat, flat, np.zeros(p.e_shape)))
+    timed("multiple", lambda: O.multiple_scattering(p, O.F32, T, flat, flat, idx))
+    scale = n_tex / idx.size
+    total = (t["transmittance"] + t["direct_irradiance"] + scale * t["single_scattering"] + scale * t["density_o2"]
+             + 2 * scale * t["density_o3"] + t["indirect_o1"] + 2 * t["indirect_o2"] + 3 * scale * t["multiple"])
+    sample = (f"oracle fp32 port (not lavapipe): 2-D stages in full, 3-D stages on every {stride}th texel "
+              f"({idx.size} of {n_tex}) scaled x{scale:.0f}; {sum(t.values()):.1f} s of CPU wall time")
+    return total * 1e3, sample
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself (Rust + GLSL on Vulkan)
+    cannot run here — no cargo, no shaderc, no Vulkan loader/ICD (lavapipe or NVIDIA) in the image — so this arm
+    times the oracle port, OpenMP over all host cores."""
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    stride = 8 * max(1, math.ceil(total / 12))
+    vals, sample = [], ""
+    for i in range(total):
+        ms, sample = cpu_precompute_ms(stride)
+        if i >= args.warmup:
+            vals.append(ms)
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "reference_unavailable": "Rust+GLSL/Vulkan reference cannot be built or run in this image (no cargo, shaderc, "
+                                     "Vulkan loader or ICD); lavapipe and B200-Vulkan baselines are unavailable"}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank: int, local_rank: int, world: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fuzzyblue_b200 as fb
+    from fuzzyblue_b200 import api, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — fuzzyblue_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    builder = fb.Builder(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # 2x the 126 MB L2
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush_buf.fill_(rank & 0xFF)
+
+    # rank r builds its own atmosphere (rank 0: the default Earth; others: seeded variations of it, same dims)
+    params = fb.Parameters() if rank == 0 else synthetic.random_atmospheres(rank, seed=20260)[-1]
+    pending = fb.Atmosphere.build(builder, stream, params)
+    stream.synchronize()
+    launches = pending.launch_count()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K replays of the recorded command stream --------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        flush_l2()
+        pending.resubmit(stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        pending.resubmit(stream)
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = ms_per_step / world          # ms per atmosphere over the whole job
+
+    # ---- end to end through the host-buffer path: params from host memory in, the three tables out to pinned host --
+    atm = pending.atmosphere()
+    P = params
+    hT = torch.empty((P.transmittance_r_size, P.transmittance_mu_size, 4), dtype=torch.float32).pin_memory()
+    hE = torch.empty((P.irradiance_r_size, P.irradiance_mu_s_size, 4), dtype=torch.float32).pin_memory()
+    hS = torch.empty((P.scattering_r_size, P.scattering_mu_size, P.scattering_nu_size * P.scattering_mu_s_size, 4),
+                     dtype=torch.float16).pin_memory()
+    L = api._lib()
+    vp = api.c_void_p
+
+    def e2e_once():
+        pending.resubmit(stream)    # the 320-byte parameter block rides in the kernel arguments of the recorded stream
+        api._check(L.fb_atmosphere_read_transmittance(atm._h, vp(hT.data_ptr()), hT.numel() * 4, api._stream(stream)))
+        api._check(L.fb_atmosphere_read_scattering(atm._h, vp(hS.data_ptr()), hS.numel() * 2, api._stream(stream)))
+        api._check(L.fb_atmosphere_read_irradiance(atm._h, vp(hE.data_ptr()), hE.numel() * 4, api._stream(stream)))
+        stream.synchronize()
+
+    for _ in range(3):
+        e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        e2e_once()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    d2h = hT.numel() * 4 + hS.numel() * 2 + hE.numel() * 4
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0, N = 1 extras: roofline of the dominant kernel, render throughput, CPU baseline -----------------
+    fma_tflops, sfu_gops = builder.measure_peaks()
+    roof = {}
+    for order in (2, 3):
+        n = 10
+        for _ in range(3):
+            pending.run_stage(api.STAGE_SCATTERING_DENSITY, order=order, stream=stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            pending.run_stage(api.STAGE_SCATTERING_DENSITY, order=order, stream=stream)
+        e1.record(stream)
+        stream.synchronize()
+        roof[order] = e0.elapsed_time(e1) / n
+    # one step launches the order-2 variant once and the order>=3 variant twice
+    dens_ms = (roof[2] + 2 * roof[3]) / 3
+    hoisted = DENSITY_SAMPLES * (FLOP_HOISTED[2] + 2 * FLOP_HOISTED[3]) / 3
+    written = DENSITY_SAMPLES * (FLOP_AS_WRITTEN[2] + 2 * FLOP_AS_WRITTEN[3]) / 3
+    achieved = hoisted / (dens_ms * 1e-3) / 1e12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+    roofline = {"kernel": "scattering_density", "bound": "fp32", "achieved": achieved, "peak": fma_tflops, "unit": "TFLOP/s",
+                "frac": achieved / fma_tflops if fma_tflops else None, "traffic": None,
+                "tally": "hoisted-minimal fp32 flops/sample (92 order 2, 63 order>=3; SURVEY.md §8d), 5.37e8 samples/launch",
+                "achieved_as_written_tflops": written / (dens_ms * 1e-3) / 1e12,
+                "peak_source": "fb_builder_measure_peaks: FFMA issue microbenchmark on this device (measured); "
+                               "MEASURED_PEAKS.json has no FP32 figure",
+                "sfu_peak_gops": sfu_gops, "ms_per_launch": {"order2": roof[2], "order3": roof[3]},
+                "share_of_step": 3 * dens_ms / ms_per_step,
+                "hbm": {"algorithmic_bytes_per_launch": 3 * 8 * 32 * 128 * 256,
+                        "achieved_gbs": 3 * 8 * 32 * 128 * 256 / (dens_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_file) else "fallback"}}
+
+    render = render_leg(args, builder, pending, stream, dev) if world == 1 else None
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample = cpu_precompute_ms(16)
+        cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "atmospheres_per_step": world, "timing": "CUDA events per step on the launch "
+                       "stream, 256 MiB L2 flush between steps (outside the events), max over ranks",
+                       "kernels": "FAST"},
+            "e2e": {"value": float(e2e_ms.item()) / world, "unit": UNIT, "h2d_bytes_per_step": 320, "d2h_bytes_per_step": d2h,
+                    "note": "graph replay + read-back of transmittance, scattering, irradiance into pinned host memory, wall clock"},
+            "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "render": render}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def render_leg(args, builder, pending, stream, dev):
+    """Second half of BASELINE.json's metric: sky evaluation at 3840x2160 over a 256-view camera sweep
+    (config[4]), in chunks of 8 views (depth + two RGBA32F outputs per chunk = 2.4 GB >> L2)."""
+    import numpy as np
+    import torch
+
+    import fuzzyblue_b200 as fb
+    from fuzzyblue_b200 import synthetic
+    W, H, VIEWS, CHUNK = 3840, 2160, args.render_views, 8
+    atm = pending.atmosphere()
+    renderer = fb.Renderer(builder)
+    draws, extra = synthetic.camera_sweep(VIEWS, W, H)
+    depth = torch.empty((CHUNK, H, W), device=dev)
+    color = torch.empty((CHUNK, H, W, 4), device=dev)
+    transm = torch.empty((CHUNK, H, W, 4), device=dev)
+
+    def make_depth(k):
+        """Analytic ground-sphere depth on the device (same construction as synthetic.analytic_depth)."""
+        inv = torch.tensor(extra[k][0], device=dev, dtype=torch.float64)
+        eye = torch.tensor(extra[k][1], device=dev, dtype=torch.float64)
+        xs = (torch.arange(W, device=dev, dtype=torch.float64) + 0.5) / W * 2 - 1
+        ys = (torch.arange(H, device=dev, dtype=torch.float64) + 0.5) / H * 2 - 1
+        ny, nx = torch.meshgrid(ys, xs, indexing="ij")
+        d = inv[:3, 0, None, None] * nx + inv[:3, 1, None, None] * ny + inv[:3, 3, None, None]
+        d = d / d.norm(dim=0)
+        R = 6360.0e3
+        b = (eye[:, None, None] * d).sum(0)
+        disc = b * b - (eye @ eye - R * R)
+        t = -b - disc.clamp_min(0).sqrt()
+        hit = (disc > 0) & (t > 0)
+        fwd = inv[:3, 3] / inv[:3, 3].norm()
+        z = t * (fwd[:, None, None] * d).sum(0)
+        return torch.where(hit, 0.1 / z.clamp_min(1e-9), torch.zeros_like(z)).float()
+
+    total_ms, px, n_launch = 0.0, 0, 0
+    for c0 in range(0, VIEWS, CHUNK):
+        n = min(CHUNK, VIEWS - c0)
+        for j in range(n):
+            depth[j] = make_depth(c0 + j)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if c0 == 0:   # warm-up
+            renderer.draw_sweep(stream, atm, draws[c0:c0 + n], depth, color, transm, W, H)
+        e0.record(stream)
+        renderer.draw_sweep(stream, atm, draws[c0:c0 + n], depth, color, transm, W, H)
+        e1.record(stream)
+        stream.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        px += n * W * H
+        n_launch += 1
+    mpx = px / (total_ms * 1e-3) / 1e6
+    # end to end for one 4K frame: depth from pinned host memory in, both RGBA32F outputs back to pinned host memory
+    hd = depth[0].cpu().pin_memory()
+    hc = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    ht = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    renderer.set_depth_buffer(0, depth[0])
+
+    def frame():
+        with torch.cuda.stream(stream):
+            depth[0].copy_(hd, non_blocking=True)
+            renderer.draw(stream, atm, 0, draws[0], color[0], transm[0], W, H)
+            hc.copy_(color[0], non_blocking=True)
+            ht.copy_(transm[0], non_blocking=True)
+        stream.synchronize()
+
+    frame()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        frame()
+    e2e_s = (time.perf_counter() - t0) / 5
+    return {"metric": "sky evaluation Mpixel/s at 3840x2160", "value": mpx, "unit": "Mpixel/s", "views": VIEWS,
+            "ms_per_frame": total_ms / VIEWS, "gpu_launches": n_launch, "inputs": "depth + outputs per 8-view chunk 2.4 GB > L2",
+            "hbm": {"bytes_per_pixel": 36, "achieved_gbs": 36 * px / (total_ms * 1e-3) / 1e9},
+            "e2e": {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4,
+                    "d2h_bytes_per_step": W * H * 32}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--render-views", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

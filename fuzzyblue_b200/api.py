@@ -96,6 +96,7 @@ ABI = {
     "fb_builder_set_kernels": (c_int, [c_void_p, c_int]),
     "fb_builder_device": (c_int, [c_void_p]),
     "fb_builder_sm_count": (c_int, [c_void_p]),
+    "fb_builder_measure_peaks": (c_int, [c_void_p, _P(ctypes.c_double), _P(ctypes.c_double)]),
     "fb_atmosphere_build": (c_int, [c_void_p, _P(FbParams), c_uint32, c_void_p, _P(c_void_p)]),
     "fb_atmosphere_allocate": (c_int, [c_void_p, _P(FbParams), c_uint32, _P(c_void_p)]),
     "fb_pending_resubmit": (c_int, [c_void_p, c_void_p]),
@@ -303,6 +304,12 @@ class Builder:
 
     def sm_count(self) -> int:
         return _lib().fb_builder_sm_count(self._h)
+
+    def measure_peaks(self) -> Tuple[float, float]:
+        """(dense FP32 FMA TFLOP/s, SFU Gop/s) measured on this device."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _check(_lib().fb_builder_measure_peaks(self._h, byref(a), byref(b)))
+        return a.value, b.value
 
     def close(self):
         if self._h:

@@ -244,6 +244,12 @@ int fb_builder_set_kernels(FbBuilder* b, int k) {
     b->kernels = k;
     return FB_OK;
 }
+int fb_builder_measure_peaks(FbBuilder* b, double* fp32_fma_tflops, double* sfu_gops) {
+    if (!b) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_measure_peaks: NULL");
+    DeviceGuard g(b->device);
+    cudaError_t e = measure_peaks(b->sm_count, fp32_fma_tflops, sfu_gops);
+    return e == cudaSuccess ? FB_OK : cuda_fail(e, "measure_peaks");
+}
 int fb_builder_device(const FbBuilder* b) { return b ? b->device : -1; }
 int fb_builder_sm_count(const FbBuilder* b) { return b ? b->sm_count : 0; }
 

@@ -72,4 +72,6 @@ cudaError_t sky_radiance(const FbParams& P, const float4* transmittance, const u
 cudaError_t sun_sky_irradiance(const FbParams& P, const float4* transmittance, const float4* irradiance, const float* point,
                                const float* normal, const float* sun, uint64_t n, float* direct, float* sky, cudaStream_t s);
 
+cudaError_t measure_peaks(int sm_count, double* fma_tflops, double* sfu_gops);
+
 }  // namespace fb

@@ -148,6 +148,9 @@ FB_API void fb_builder_destroy(FbBuilder* b);
 FB_API int fb_builder_set_kernels(FbBuilder* b, int kernels /* FbKernels */);
 FB_API int fb_builder_device(const FbBuilder* b);
 FB_API int fb_builder_sm_count(const FbBuilder* b);
+/* Measured issue-rate ceilings of this device (dense FP32 FMA TFLOP/s, SFU Gop/s): the roofline
+ * denominators of this transcendental-heavy path (no reference analogue). Takes ~50 ms. */
+FB_API int fb_builder_measure_peaks(FbBuilder* b, double* fp32_fma_tflops, double* sfu_gops);
 
 /* Atmosphere::build, src/precompute.rs:1077-2073: allocate the 3 kept + 5 temporary images and
  * enqueue the whole command stream of :1671-2048 on `stream`. */

@@ -446,22 +446,23 @@ template <class R> struct Oracle {
         ray = rs * dx * solar_irradiance * rayleigh_scattering;
         mie = ms * dx * solar_irradiance * mie_scattering;
     }
-    void single_scattering_pass(const Table<R>& T, Table<R>& dR, Table<R>& dM, Table<R>& S) const {  // :89-101
+    // :89-101; idx == nullptr -> every texel, else the n linear texel indices (outputs are [n][4] rows)
+    void single_scattering_texels(const Table<R>& T, const int64_t* idx, int64_t n, double* dR, double* dM, double* S) const {
         int W = S_nu * S_mu_s;
-        dR.resize(W, S_mu, S_r); dM.resize(W, S_mu, S_r); S.resize(W, S_mu, S_r);
-#pragma omp parallel for collapse(2) schedule(dynamic, 4)
-        for (int z = 0; z < S_r; ++z)
-            for (int y = 0; y < S_mu; ++y)
-                for (int x = 0; x < W; ++x) {
-                    R r, mu, mu_s, nu; bool hits;
-                    TexelToRMuMuSNu(x, y, z, r, mu, mu_s, nu, hits);
-                    V3<R> ray, mie;
-                    SingleScatteringAt(T, r, mu, mu_s, nu, hits, ray, mie);
-                    R* a = dR.at(x, y, z); R* b = dM.at(x, y, z); R* c = S.at(x, y, z);
-                    a[0] = store16(ray.x); a[1] = store16(ray.y); a[2] = store16(ray.z); a[3] = R(0);
-                    b[0] = store16(mie.x); b[1] = store16(mie.y); b[2] = store16(mie.z); b[3] = R(0);
-                    c[0] = a[0]; c[1] = a[1]; c[2] = a[2]; c[3] = b[0];
-                }
+        int64_t total = idx ? n : int64_t(W) * S_mu * S_r;
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t k = 0; k < total; ++k) {
+            int64_t lin = idx ? idx[k] : k;
+            unsigned x = unsigned(lin % W), y = unsigned((lin / W) % S_mu), z = unsigned(lin / (int64_t(W) * S_mu));
+            R r, mu, mu_s, nu; bool hits;
+            TexelToRMuMuSNu(x, y, z, r, mu, mu_s, nu, hits);
+            V3<R> ray, mie;
+            SingleScatteringAt(T, r, mu, mu_s, nu, hits, ray, mie);
+            double* a = dR + k * 4; double* b = dM + k * 4; double* c = S + k * 4;
+            a[0] = double(store16(ray.x)); a[1] = double(store16(ray.y)); a[2] = double(store16(ray.z)); a[3] = 0.0;
+            b[0] = double(store16(mie.x)); b[1] = double(store16(mie.y)); b[2] = double(store16(mie.z)); b[3] = 0.0;
+            c[0] = a[0]; c[1] = a[1]; c[2] = a[2]; c[3] = b[0];
+        }
     }
 
     // --- shaders/scattering_density.comp -----------------------------------------------------
@@ -642,9 +643,9 @@ template <class R> struct Run {
     void direct_irradiance(const double* T, double* dE) {
         Table<R> t, e; load(t, T, o.T_mu, o.T_r, 1); o.direct_irradiance_pass(t, e); save(e, dE);
     }
-    void single_scattering(const double* T, double* dR, double* dM, double* S) {
-        Table<R> t, a, b, c; load(t, T, o.T_mu, o.T_r, 1);
-        o.single_scattering_pass(t, a, b, c); save(a, dR); save(b, dM); save(c, S);
+    void single_scattering(const double* T, const int64_t* idx, int64_t n, double* dR, double* dM, double* S) {
+        Table<R> t; load(t, T, o.T_mu, o.T_r, 1);
+        o.single_scattering_texels(t, idx, n, dR, dM, S);
     }
     // texel subset: idx == nullptr -> every texel (n ignored), out is [n][4] or the whole table
     void scattering_density(const double* T, const double* dR, const double* dM, const double* dMS,
@@ -789,8 +790,9 @@ int fbo_transmittance(const void* params, int mode, double* T) {
 int fbo_direct_irradiance(const void* params, int mode, const double* T, double* dE) {
     return dispatch(params, mode, [&](auto& r) { r.direct_irradiance(T, dE); });
 }
-int fbo_single_scattering(const void* params, int mode, const double* T, double* dR, double* dM, double* S) {
-    return dispatch(params, mode, [&](auto& r) { r.single_scattering(T, dR, dM, S); });
+int fbo_single_scattering(const void* params, int mode, const double* T, const int64_t* idx, int64_t n, double* dR,
+                          double* dM, double* S) {
+    return dispatch(params, mode, [&](auto& r) { r.single_scattering(T, idx, n, dR, dM, S); });
 }
 int fbo_scattering_density(const void* params, int mode, int order, const double* T, const double* dR,
                            const double* dM, const double* dMS, const double* dE, const int64_t* idx, int64_t n,

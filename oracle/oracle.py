@@ -50,7 +50,7 @@ def lib():
         L.fbo_round_to_half.argtypes = [ctypes.c_double]
         L.fbo_transmittance.argtypes = [vp, ci, d]
         L.fbo_direct_irradiance.argtypes = [vp, ci, d, d]
-        L.fbo_single_scattering.argtypes = [vp, ci, d, d, d, d]
+        L.fbo_single_scattering.argtypes = [vp, ci, d, i64, c64, d, d, d]
         L.fbo_scattering_density.argtypes = [vp, ci, ci, d, d, d, d, d, i64, c64, d]
         L.fbo_indirect_irradiance.argtypes = [vp, ci, ci, d, d, d, d, d]
         L.fbo_multiple_scattering.argtypes = [vp, ci, d, d, i64, c64, d, d]
@@ -168,10 +168,12 @@ def direct_irradiance(p: Params, mode: int, T) -> np.ndarray:
     return dE
 
 
-def single_scattering(p: Params, mode: int, T):
+def single_scattering(p: Params, mode: int, T, idx=None):
     T = _c(T)
-    dR, dM, S = np.zeros(p.s_shape), np.zeros(p.s_shape), np.zeros(p.s_shape)
-    assert lib().fbo_single_scattering(p.pack(), mode, _p(T), _p(dR), _p(dM), _p(S)) == 0
+    ip, n, keep = _idx(idx)
+    shape = p.s_shape if idx is None else (n, 4)
+    dR, dM, S = np.zeros(shape), np.zeros(shape), np.zeros(shape)
+    assert lib().fbo_single_scattering(p.pack(), mode, _p(T), ip, n, _p(dR), _p(dM), _p(S)) == 0
     return dR, dM, S
 
 
