@@ -1,16 +1,655 @@
-// fb_kernels_fast.cu — FB_KERNELS_FAST (placeholder while the restructured kernels land: forwards
-// to the reference family so the ABI is complete).
+// fb_kernels_fast.cu — FB_KERNELS_FAST: the product kernels for sm_100a.
+//
+// Same shaders, same quadrature nodes, same image formats as fb_kernels_ref.cu; what changes is
+// *where* each quantity is computed.  Rule of the house (DESIGN.md "Numerics"):
+//   * every ill-conditioned scalar (ray lengths, discriminants, r*r - bottom*bottom, texel -> (r,mu,mu_s,nu))
+//     is evaluated in fb::xf exactly as the GLSL writes it — those cancel catastrophically and a
+//     different rounding moves a texel by per cents;
+//   * anything that is invariant across a block (per-r, per-(r,theta), per-(r,mu) quantities, whole
+//     interpolated table rows) is computed once, bit-identically, and shared through shared memory;
+//   * only convex interpolation, phase functions and the accumulation of positive terms run in plain
+//     fp32 with FMA contraction and a different summation order (relative effect ~1e-7).
 #include "fb_kernels.h"
+#include "fb_shader_math.cuh"
 
 namespace fb {
 namespace fast {
-size_t scratch_bytes(const FbParams&) { return 0; }
-cudaError_t transmittance(const LaunchCtx& c) { return ref::transmittance(c); }
-cudaError_t direct_irradiance(const LaunchCtx& c) { return ref::direct_irradiance(c); }
-cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) { return ref::single_scattering(c, r0, r1); }
-cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1) { return ref::scattering_density(c, order, r0, r1); }
-cudaError_t indirect_irradiance(const LaunchCtx& c, int order) { return ref::indirect_irradiance(c, order); }
-cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) { return ref::multiple_scattering(c, r0, r1); }
-int launches_per_stage(int) { return 1; }
+
+typedef xf F;
+typedef V3<xf> V;
+
+static inline Tex2 tex2(const float4* p, int w, int h) { Tex2 t; t.p = p; t.w = w; t.h = h; return t; }
+static inline Tex3 tex3(const uint2* p, int w, int h, int d) { Tex3 t; t.p = p; t.w = w; t.h = h; t.d = d; return t; }
+static inline Tex2 texT(const LaunchCtx& c) { return tex2(c.img.transmittance, c.P.transmittance_mu_size, c.P.transmittance_r_size); }
+static inline Tex3 texS(const LaunchCtx& c, const uint2* p) {
+    return tex3(p, c.P.scattering_nu_size * c.P.scattering_mu_s_size, c.P.scattering_mu_size, c.P.scattering_r_size);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers: mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+/sm_100a
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// scattering_density.comp — the dominant kernel (~90 % of the reference's work).
+//
+// For a texel (r, mu, mu_s, nu) the shader sums, over 16 theta x 32 phi directions w_i,
+//     L(r, cos theta, mu_s, nu1 = w_s . w_i) * Phase(nu2 = w . w_i) * dw
+// and inside that loop re-derives, per sample, quantities that do not depend on the sample:
+//   * the 4-D look-up coordinates u_r(r), u_mu(r, theta), u_mu_s(mu_s)  — only u_nu(nu1) varies;
+//   * the phase/extinction weight — a function of (r, mu, theta, phi) only, shared by the whole
+//     (mu_s, nu) plane of the table;
+//   * the ground term's transmittance, distance and normal — functions of (r, theta[, phi]).
+// Layout here:
+//   k_density_prep   once per order, per r: for every (theta_l, mu_s, nu-slice k) the trilinear tap the shader
+//                    would take (exact, as written) -> a [r][tile][l][mu_s][k] table in global scratch (2 MiB at
+//                    default dims; x2 at order 2 where Rayleigh and Mie are looked up separately), plus the
+//                    per-(r, theta) ground constants.
+//   k_density_main   one CTA per (r, mu, mu_s-tile): the CTA's 64 / 128 KiB slice of that table arrives by ONE
+//                    TMA bulk copy (cp.async.bulk + mbarrier) while the CTA computes texel geometry and the 512
+//                    phase weights.  Then one WARP per texel, lane = phi index (32 lanes = the 32 phi samples),
+//                    unrolled loop over the 16 theta: per sample 2 LDS.128 from one 128-byte table row
+//                    (one wavefront: every lane reads the same (l, mu_s) row), a nu-lerp and 3 FMAs against the
+//                    lane's register-resident weights; the phi-sum is a 5-step __shfl_xor tree.
+// ---------------------------------------------------------------------------------------------
+constexpr int DL = 16;   // theta samples, scattering_density.comp:34
+
+struct DensityDims {
+    int nu, ms_tile, tiles, T;   // T = ms_tile * nu texels per CTA (<= 256)
+};
+static inline DensityDims density_dims(const FbParams& P) {
+    DensityDims d;
+    d.nu = P.scattering_nu_size;
+    int want = 256 / d.nu;
+    if (want < 1) want = 1;
+    d.ms_tile = P.scattering_mu_s_size < want ? P.scattering_mu_s_size : want;
+    d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
+    d.T = d.ms_tile * d.nu;
+    return d;
+}
+// floats of scratch: table [R][tiles][DL][T][E] float4  +  ground [R][DL][2] float4
+static inline size_t density_tab_float4(const FbParams& P) {
+    DensityDims d = density_dims(P);
+    return (size_t)P.scattering_r_size * d.tiles * DL * d.T * 2;
+}
+
+size_t scratch_bytes(const FbParams& P) {
+    return (density_tab_float4(P) + (size_t)P.scattering_r_size * DL * 2) * sizeof(float4);
+}
+
+template <bool ORDER2>
+__global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
+                                                      Tex3 A0, Tex3 A1, DensityDims dd, float4* __restrict__ tab,
+                                                      float4* __restrict__ gnd, int r0) {
+    constexpr int E = ORDER2 ? 2 : 1;
+    const int l = blockIdx.y, z = r0 + blockIdx.z;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    if (e >= W) return;
+    const int k = e % dd.nu, ms = e / dd.nu;
+    A<F> a(P);
+    F r, mu_unused, mu_s, nu_unused;
+    bool hits_unused;
+    // r and mu_s exactly as the consuming texels derive them (scattering.h:116-137)
+    a.TexelToRMuMuSNu((unsigned)ms, 0u, (unsigned)z, r, mu_unused, mu_s, nu_unused, hits_unused);
+    const F ct = F(tg.ct16[l]), st = F(tg.st16[l]);
+    const bool hits = a.RayIntersectsGround(r, ct);                                   // scattering_density.comp:45-46
+    F uvwz[4];
+    a.ScatteringUvwz(r, ct, mu_s, F(0.f), hits, uvwz);                                // scattering.h:144-145
+    const F nn = F((float)dd.nu);
+    const F ux = (F((float)k) + uvwz[1]) / nn;                                        // scattering.h:149
+    const int tile = ms / dd.ms_tile, msl = ms % dd.ms_tile;
+    const size_t o = ((((size_t)z * dd.tiles + tile) * DL + l) * dd.T + (size_t)msl * dd.nu + k) * E;
+    V4<F> s0 = sample<F>(A0, ux, uvwz[2], uvwz[3]);
+    tab[o] = make_float4(s0.x.v, s0.y.v, s0.z.v, 0.f);
+    if (ORDER2) {
+        V4<F> s1 = sample<F>(A1, ux, uvwz[2], uvwz[3]);
+        tab[o + 1] = make_float4(s1.x.v, s1.y.v, s1.z.v, 0.f);
+    }
+    if (e == 0) {   // per-(r, theta) ground constants, scattering_density.comp:50-60, :81-87
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+        if (hits) {
+            F dg = a.DistanceToBottom(r, ct);
+            V tgr = a.Transmittance(T, r, ct, dg, true);
+            V G = tgr * V(P.ground_albedo) * (F(1.f) / F(FB_PI_F));
+            // |zenith*r + w_i*dg| does not depend on phi: (st*dg)^2 + (r + ct*dg)^2
+            F vx = st * dg, vz = r + ct * dg;
+            F len = f_sqrt(vx * vx + vz * vz);
+            g0 = make_float4(1.f, (dg / len).v, (vz / len).v, 0.f);
+            g1 = make_float4(G.x.v, G.y.v, G.z.v, 0.f);
+        }
+        gnd[((size_t)z * DL + l) * 2] = g0;
+        gnd[((size_t)z * DL + l) * 2 + 1] = g1;
+    }
+}
+
+template <bool ORDER2, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, ORDER2 ? 1 : 2)
+k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float4* __restrict__ tabG,
+               const float4* __restrict__ gndG, const float4* __restrict__ dE_row0, uint2* __restrict__ out, int r0) {
+    constexpr int E = ORDER2 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [table: DL*T*E float4][geo: T float4][outS: T float4][Wt: DL*32 float4][gnd: DL*2 float4][Erow: n float4][mbar]
+    float4* tabS = reinterpret_cast<float4*>(smem_raw);
+    float4* geoS = tabS + (size_t)DL * dd.T * E;
+    float4* outS = geoS + dd.T;
+    float4* WtS = outS + dd.T;
+    float4* gndS = WtS + DL * 32;
+    float4* ErowS = gndS + DL * 2;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ErowS + P.irradiance_mu_s_size);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    const uint32_t tab_bytes = (uint32_t)(DL * dd.T * E * sizeof(float4));
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, tab_bytes);
+        tma_bulk_g2s(tabS, tabG + ((size_t)z * dd.tiles + tile) * DL * dd.T * E, tab_bytes, bar);
+    }
+
+    A<F> a(P);
+    // ---- texel geometry, exact (scattering_density.comp:28-32) ------------------------------------------
+    F r, mu;
+    for (int t = tid; t < dd.T; t += NWARPS * 32) {
+        const int nui = t / dd.ms_tile, msl = t % dd.ms_tile;
+        const int ms = tile * dd.ms_tile + msl;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ms < P.scattering_mu_s_size) {
+            F mu_s, nu;
+            bool hu;
+            a.TexelToRMuMuSNu((unsigned)(nui * P.scattering_mu_s_size + ms), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hu);
+            F ox = f_sqrt(F(1.f) - mu * mu);
+            F sx = ox == F(0.f) ? F(0.f) : (nu - mu * mu_s) / ox;
+            F sy = f_sqrt(f_max(F(1.f) - sx * sx - mu_s * mu_s, F(0.f)));
+            g = make_float4(sx.v, sy.v, mu_s.v, __int_as_float(msl * dd.nu * E));
+        }
+        geoS[t] = g;
+    }
+    {   // r and mu of this CTA's row (independent of x)
+        F ms_u, nu_u;
+        bool hu;
+        a.TexelToRMuMuSNu(0u, (unsigned)y, (unsigned)z, r, mu, ms_u, nu_u, hu);
+    }
+    // ---- the 512 phase weights of this (r, mu) row, once per CTA (scattering_density.comp:93-103) -------
+    {
+        const F ox = f_sqrt(F(1.f) - mu * mu);
+        const F ray_rho = A<F>::ProfileDensity(P.rayleigh_density, r - a.bottom());
+        const F mie_rho = A<F>::ProfileDensity(P.mie_density, r - a.bottom());
+        const F dphi = F(FB_PI_F) / F(16.f), dtheta = F(FB_PI_F) / F(16.f);
+        for (int e = tid; e < DL * 32; e += NWARPS * 32) {
+            const int l = e >> 5, m = e & 31;
+            const F st = F(tg.st16[l]), ct = F(tg.ct16[l]);
+            const F wix = F(tg.cp32[m]) * st, wiy = F(tg.sp32[m]) * st;
+            const F nu2 = ox * wix + F(0.f) * wiy + mu * ct;
+            const F dw = dtheta * dphi * st;
+            const F pr = A<F>::RayleighPhase(nu2), pm = A<F>::MiePhase(F(P.mie_phase_function_g), nu2);
+            V w = (V(P.rayleigh_scattering) * ray_rho * pr + V(P.mie_scattering) * mie_rho * pm) * dw;
+            WtS[e] = make_float4(w.x.v, w.y.v, w.z.v, 0.f);
+        }
+    }
+    for (int e = tid; e < DL * 2; e += NWARPS * 32) gndS[e] = __ldg(gndG + (size_t)z * DL * 2 + e);
+    for (int e = tid; e < P.irradiance_mu_s_size; e += NWARPS * 32) ErowS[e] = __ldg(dE_row0 + e);
+    __syncthreads();
+
+    // ---- per-lane constants: direction components and weights of phi sample `lane` ------------------------
+    float wx[DL], wy[DL], Wr[DL], Wg[DL], Wb[DL];
+    uint32_t gmask = 0;
+#pragma unroll
+    for (int l = 0; l < DL; ++l) {
+        wx[l] = __fmul_rn(tg.cp32[lane], tg.st16[l]);
+        wy[l] = __fmul_rn(tg.sp32[lane], tg.st16[l]);
+        float4 w = WtS[l * 32 + lane];
+        Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
+        if (gndS[l * 2].x != 0.f) gmask |= 1u << l;
+    }
+    const float hn = 0.5f * (float)(dd.nu - 1);
+    const float tmax = __int_as_float(__float_as_int((float)(dd.nu - 1)) - 1);   // largest float below nu-1
+    const float MAGIC = 8388608.f;
+    const int nE = P.irradiance_mu_s_size;
+    // GetIrradiance at r = bottom: v lands on row 0; u*N - 0.5 = (0.5/N + x(1 - 1/N))*N - 0.5 with x = mu_s*0.5 + 0.5
+    const float e_c1 = 0.5f * (float)(nE - 1), e_c0 = 0.5f * (float)(nE - 1);
+    const float e_max = __int_as_float(__float_as_int((float)(nE - 1)) - 1);
+    float kR = 0.f, kMR = 0.f, g2p1 = 0.f, m2g = 0.f;
+    if (ORDER2) {
+        const float g = P.mie_phase_function_g;
+        kR = 3.f / (16.f * FB_PI_F);
+        const float kM = 3.f / (8.f * FB_PI_F) * (1.f - g * g) / (2.f + g * g);
+        kMR = kM / kR;
+        g2p1 = 1.f + g * g;
+        m2g = -2.f * g;
+    }
+
+    mbar_wait(bar, 0);
+
+    // ---- one warp per texel, lane = phi sample -------------------------------------------------------------
+    for (int t = warp; t < dd.T; t += NWARPS) {
+        const float4 geo = geoS[t];
+        const float sx = geo.x, sy = geo.y, mus = geo.z;
+        const float4* row_t = tabS + __float_as_int(geo.w);
+        float ar = 0.f, ag = 0.f, ab = 0.f;
+#pragma unroll
+        for (int l = 0; l < DL; ++l) {
+            const float h = fmaf(sx, wx[l], sy * wy[l]);
+            const float nu1 = fmaf(mus, tg.ct16[l], h);
+            float tcx = fminf(fmaxf(fmaf(nu1, hn, hn), 0.f), tmax);              // scattering.h:146
+            const float tm = __fadd_rd(tcx, MAGIC);
+            const int k = __float_as_int(tm) - 0x4B000000;                        // floor(tcx)
+            const float f = tcx - (tm - MAGIC);
+            const float4* p = row_t + (size_t)l * dd.T * E + k * E;
+            float Lr, Lg, Lb;
+            if (ORDER2) {
+                const float4 r0v = p[0], m0v = p[1], r1v = p[2], m1v = p[3];
+                const float pr = fmaf(nu1 * kR, nu1, kR);                         // util.h:26-29
+                const float base = fmaf(m2g, nu1, g2p1);
+                const float rs = rsqrtf(base);
+                const float pm = pr * kMR * (rs * rs * rs);                       // util.h:31-34, x^-1.5 = rsqrt(x)^3
+                const float rr = fmaf(f, r1v.x - r0v.x, r0v.x), rg = fmaf(f, r1v.y - r0v.y, r0v.y), rb = fmaf(f, r1v.z - r0v.z, r0v.z);
+                const float mr = fmaf(f, m1v.x - m0v.x, m0v.x), mg = fmaf(f, m1v.y - m0v.y, m0v.y), mb = fmaf(f, m1v.z - m0v.z, m0v.z);
+                Lr = fmaf(mr, pm, rr * pr); Lg = fmaf(mg, pm, rg * pr); Lb = fmaf(mb, pm, rb * pr);
+            } else {
+                const float4 v0 = p[0], v1 = p[1];
+                Lr = fmaf(f, v1.x - v0.x, v0.x); Lg = fmaf(f, v1.y - v0.y, v0.y); Lb = fmaf(f, v1.z - v0.z, v0.z);
+            }
+            if (gmask & (1u << l)) {                                              // warp-uniform
+                const float4 g0 = gndS[l * 2], G = gndS[l * 2 + 1];
+                const float musg = fmaf(h, g0.y, mus * g0.z);                     // dot(ground_normal, omega_s)
+                float te = fminf(fmaxf(fmaf(musg, e_c1, e_c0), 0.f), e_max);      // irradiance.h:20-30 at r = bottom
+                const float em = __fadd_rd(te, MAGIC);
+                const int j = __float_as_int(em) - 0x4B000000;
+                const float fe = te - (em - MAGIC);
+                const float4 e0 = ErowS[j], e1 = ErowS[j + 1];
+                Lr = fmaf(G.x, fmaf(fe, e1.x - e0.x, e0.x), Lr);
+                Lg = fmaf(G.y, fmaf(fe, e1.y - e0.y, e0.y), Lg);
+                Lb = fmaf(G.z, fmaf(fe, e1.z - e0.z, e0.z), Lb);
+            }
+            ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, s);
+            ag += __shfl_xor_sync(0xffffffffu, ag, s);
+            ab += __shfl_xor_sync(0xffffffffu, ab, s);
+        }
+        if (lane == 0) outS[t] = make_float4(ar, ag, ab, 0.f);
+    }
+    __syncthreads();
+    for (int t = tid; t < dd.T; t += NWARPS * 32) {
+        const int nui = t / dd.ms_tile, ms = tile * dd.ms_tile + t % dd.ms_tile;
+        if (ms < P.scattering_mu_s_size) {
+            const float4 v = outS[t];
+            out[((size_t)z * P.scattering_mu_size + y) * W + nui * P.scattering_mu_s_size + ms] = pack_half4(v.x, v.y, v.z, 0.f);
+        }
+    }
+}
+
+static size_t density_smem(const FbParams& P, const DensityDims& d, bool order2) {
+    return ((size_t)DL * d.T * (order2 ? 2 : 1) + 2 * d.T + DL * 32 + DL * 2 + P.irradiance_mu_s_size) * sizeof(float4) + 16;
+}
+
+cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1) {
+    const FbParams& P = c.P;
+    DensityDims d = density_dims(P);
+    const bool o2 = order == 2;
+    const size_t smem = density_smem(P, d, o2);
+    if (P.scattering_nu_size < 2 || smem > 220 * 1024 || !c.img.scratch) return ref::scattering_density(c, order, r0, r1);
+    float4* tab = reinterpret_cast<float4*>(c.img.scratch);
+    float4* gnd = tab + density_tab_float4(P);
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    dim3 gp((W + 255) / 256, DL, r1 - r0);
+    dim3 gm(d.tiles, P.scattering_mu_size, r1 - r0);
+    cudaError_t e;
+    if (o2) {
+        k_density_prep<true><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), d, tab, gnd, r0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_density_main<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_density_main<true, 16><<<gm, 16 * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance, c.img.scattering_density, r0);
+    } else {
+        k_density_prep<false><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), texS(c, c.img.delta_multiple_scattering),
+                                                         texS(c, c.img.delta_multiple_scattering), d, tab, gnd, r0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_density_main<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_density_main<false, 8><<<gm, 8 * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance, c.img.scattering_density, r0);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// transmittance.comp — one WARP per texel: the 501 trapezoid nodes are strided over the lanes (the
+// reference walks them serially in one thread: 16 384 threads x 1 503 dependent steps, latency-bound on 148
+// SMs), the square root is shared by the three density profiles, the three partial sums meet in a
+// __shfl_xor tree.  Per-node arithmetic is the shader's, in xf.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transmittance(const __grid_constant__ FbParams P, float4* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int texel = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int W = P.transmittance_mu_size;
+    if (texel >= W * P.transmittance_r_size) return;                                   // warp-uniform
+    const int x = texel % W, y = texel / W;
+    A<F> a(P);
+    F r, mu;
+    a.RMuFromUnitRanges(F((float)x) / F((float)(W - 1)), F((float)y) / F((float)(P.transmittance_r_size - 1)), r, mu);
+    const int N = 500;                                                                 // transmittance.comp:14
+    const F dx = a.DistanceToTop(r, mu) / F((float)N);
+    const F c2 = F(2.f) * r * mu, rr = r * r;
+    F sR = F(0.f), sM = F(0.f), sA = F(0.f);
+    for (int i = lane; i <= N; i += 32) {
+        const F d_i = F((float)i) * dx;
+        const F r_i = f_sqrt(d_i * d_i + c2 * d_i + rr);
+        const F h = r_i - a.bottom();
+        const F w_i = (i == 0 || i == N) ? F(0.5f) : F(1.f);
+        sR += A<F>::ProfileDensity(P.rayleigh_density, h) * w_i * dx;
+        sM += A<F>::ProfileDensity(P.mie_density, h) * w_i * dx;
+        sA += A<F>::ProfileDensity(P.absorption_density, h) * w_i * dx;
+    }
+    float fR = sR.v, fM = sM.v, fA = sA.v;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        fR += __shfl_xor_sync(0xffffffffu, fR, s);
+        fM += __shfl_xor_sync(0xffffffffu, fM, s);
+        fA += __shfl_xor_sync(0xffffffffu, fA, s);
+    }
+    if (lane == 0) {
+        V tau = V(P.rayleigh_scattering) * F(fR) + V(P.mie_extinction) * F(fM) + V(P.absorption_extinction) * F(fA);
+        out[texel] = make_float4(expf(-tau.x.v), expf(-tau.y.v), expf(-tau.z.v), 1.f);
+    }
+}
+
+cudaError_t transmittance(const LaunchCtx& c) {
+    const int texels = c.P.transmittance_mu_size * c.P.transmittance_r_size;
+    k_transmittance<<<(texels + 7) / 8, 256, 0, c.stream>>>(c.P, c.img.transmittance);
+    return cudaGetLastError();
+}
+
+cudaError_t direct_irradiance(const LaunchCtx& c) { return ref::direct_irradiance(c); }   // 1 024 threads, one tap each
+
+// ---------------------------------------------------------------------------------------------
+// indirect_irradiance.comp — one WARP per texel (1 024 texels x 1 024 directions: one thread per texel
+// would leave 140 SMs idle).  Lane i takes phi samples i and i+32 of every theta row; each sample is the
+// shader's 4-D look-up, as written, in xf; the hemisphere sum is a __shfl_xor tree.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_indirect_irradiance(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg,
+                                                             Tex3 dR, Tex3 dM, Tex3 dMS, int order, float4* __restrict__ dE,
+                                                             float4* __restrict__ E) {
+    const int lane = threadIdx.x & 31;
+    const int texel = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int W = P.irradiance_mu_s_size;
+    if (texel >= W * P.irradiance_r_size) return;
+    const int x = texel % W, y = texel / W;
+    A<F> a(P);
+    F r, mu_s;
+    a.RMuSFromIrradianceUnit(F((float)x) / F((float)(W - 1)), F((float)y) / F((float)(P.irradiance_r_size - 1)), r, mu_s);
+    const F dphi = F(FB_PI_F) / F(32.f), dtheta = F(FB_PI_F) / F(32.f);
+    const V omega_s(f_sqrt(F(1.f) - mu_s * mu_s), F(0.f), mu_s);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int j = 0; j < 16; ++j) {
+        const F ct = F(tg.ct32[j]), st = F(tg.st32[j]);
+        const F dw = dtheta * dphi * st;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = lane + 32 * half;
+            const V w(F(tg.cp64[i]) * st, F(tg.sp64[i]) * st, ct);
+            const F nu = dot(w, omega_s);
+            const V t = a.ScatteringOrder(dR, dM, dMS, r, w.z, mu_s, nu, false, order) * w.z * dw;
+            ax += t.x.v; ay += t.y.v; az += t.z.v;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, s);
+        ay += __shfl_xor_sync(0xffffffffu, ay, s);
+        az += __shfl_xor_sync(0xffffffffu, az, s);
+    }
+    if (lane == 0) {
+        dE[texel] = make_float4(ax, ay, az, 0.f);                                      // indirect_irradiance.comp:72
+        const float4 e = E[texel];                                                     // :73
+        E[texel] = make_float4(__fadd_rn(ax, e.x), __fadd_rn(ay, e.y), __fadd_rn(az, e.z), __fadd_rn(0.f, e.w));
+    }
+}
+
+cudaError_t indirect_irradiance(const LaunchCtx& c, int order) {
+    const int texels = c.P.irradiance_mu_s_size * c.P.irradiance_r_size;
+    k_indirect_irradiance<<<(texels + 3) / 4, 128, 0, c.stream>>>(c.P, c.trig, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie),
+                                                                   texS(c, c.img.delta_multiple_scattering), order,
+                                                                   c.img.delta_irradiance, c.img.irradiance);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// single_scattering.comp / multiple_scattering.comp — one CTA per (r, mu) row of the table, one thread per
+// (nu, mu_s) texel of the row.  The 51 trapezoid nodes of a ray depend on (r, mu) only, so everything the
+// shader recomputes per texel from (r, mu, d_i) — the node radius r_d, both transmittance look-ups of
+// GetTransmittance(r, mu, d_i), the density profiles, the horizon terms of GetTransmittanceToSun, the
+// (mu, r) interpolation cell of the 4-D look-up — is evaluated ONCE per node by thread i, exactly as written,
+// and shared through shared memory.  What stays per texel and node is the sun-angle part.
+// ---------------------------------------------------------------------------------------------
+constexpr int NS = 51;   // SAMPLE_COUNT + 1, single_scattering.comp:42 / multiple_scattering.comp:21
+
+struct SingleNode {      // per trapezoid node, block-uniform
+    float d, r_d, rd2, d_min, span, e0, e1, cos_h, v;   // v: transmittance-table row coordinate of r_d
+    float tr[3];                                           // GetTransmittance(r, mu, d_i)
+    float rho_r, rho_m;                                    // density * trapezoid weight
+};
+
+__global__ void __launch_bounds__(1024) k_single_scattering(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
+                                                            uint2* __restrict__ dM, uint2* __restrict__ S, int r0) {
+    __shared__ SingleNode nodes[NS];
+    __shared__ float s_dx;
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    const int x = threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
+    A<F> a(P);
+    F r, mu, mu_s, nu;
+    bool hits;
+    a.TexelToRMuMuSNu((unsigned)min(x, W - 1), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);
+    const F H = f_sqrt(a.top() * a.top() - a.bottom() * a.bottom());
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+        const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);
+        const F d = F((float)i) * dx;
+        const F r_d = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));      // single_scattering.comp:16
+        const V tr = a.Transmittance(T, r, mu, d, hits);                                // :19-21
+        SingleNode n;
+        n.d = d.v; n.r_d = r_d.v; n.rd2 = (r_d * r_d).v;
+        // GetTransmittanceToSun(r_d, .) and GetTransmittanceTextureUvFromRMu(r_d, .): the r_d-only parts
+        const F rho = A<F>::SafeSqrt(r_d * r_d - a.bottom() * a.bottom());              // transmittance.h:14
+        const F d_min = a.top() - r_d, d_max = rho + H;
+        n.d_min = d_min.v; n.span = (d_max - d_min).v;
+        n.v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size).v;                   // transmittance.h:21-23
+        const F sin_h = a.bottom() / r_d;                                               // transmittance.h:67-73
+        n.cos_h = (-f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)))).v;
+        const F al = F(P.sun_angular_radius);
+        const F e0 = -sin_h * al, e1 = sin_h * al;
+        n.e0 = e0.v; n.e1 = e1.v;
+        n.tr[0] = tr.x.v; n.tr[1] = tr.y.v; n.tr[2] = tr.z.v;
+        const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);                         // a power of two: folding it is exact
+        n.rho_r = (A<F>::ProfileDensity(P.rayleigh_density, r_d - a.bottom()) * w).v;   // :24-27
+        n.rho_m = (A<F>::ProfileDensity(P.mie_density, r_d - a.bottom()) * w).v;
+        nodes[i] = n;
+        if (i == 0) s_dx = dx.v;
+    }
+    __syncthreads();
+    if (x >= W) return;
+    const F r_mu_s = r * mu_s;
+    const F tt = a.top() * a.top();
+    V rs(F(0.f)), ms(F(0.f));
+    for (int i = 0; i < NS; ++i) {
+        const SingleNode& n = nodes[i];
+        const F r_d = F(n.r_d);
+        const F mu_s_d = A<F>::ClampCosine((r_mu_s + F(n.d) * nu) / r_d);               // :17
+        // DistanceToTopAtmosphereBoundary(r_d, mu_s_d), params.h:105-110
+        const F disc = F(n.rd2) * (mu_s_d * mu_s_d - F(1.f)) + tt;
+        const F dtop = A<F>::ClampDistance(-r_d * mu_s_d + A<F>::SafeSqrt(disc));
+        const F u = A<F>::CoordFromUnit((dtop - F(n.d_min)) / F(n.span), P.transmittance_mu_size);
+        const V tsun = sample<F>(T, u, F(n.v)).rgb() * f_smoothstep<F>(F(n.e0), F(n.e1), mu_s_d - F(n.cos_h));
+        const V t = V(F(n.tr[0]), F(n.tr[1]), F(n.tr[2])) * tsun;
+        rs = rs + t * F(n.rho_r);
+        ms = ms + t * F(n.rho_m);
+    }
+    const F dx = F(s_dx);
+    const V ray = rs * dx * V(P.solar_irradiance) * V(P.rayleigh_scattering);           // :62-64
+    const V mie = ms * dx * V(P.solar_irradiance) * V(P.mie_scattering);
+    const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
+    dR[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, 0.f);
+    dM[o] = pack_half4(mie.x.v, mie.y.v, mie.z.v, 0.f);
+    S[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, mie.x.v);
+}
+
+cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
+    const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
+    if (W > 1024) return ref::single_scattering(c, r0, r1);
+    const int nt = ((W + 31) / 32) * 32;
+    dim3 g(1, c.P.scattering_mu_size, r1 - r0);
+    k_single_scattering<<<g, nt, 0, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0);
+    return cudaGetLastError();
+}
+
+struct MultiNode {       // per trapezoid node, block-uniform
+    float d, inv_r;      // node distance, 1 / r_i
+    float trw[3];        // GetTransmittance(r, mu, d_i) * dx * trapezoid weight
+    float fy, fz;        // (mu, r) interpolation cell of GetScattering(r_i, mu_i, ., ., hits)
+    int y0, y1, z0, z1;
+};
+
+__global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
+                                                              uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MultiNode* nodes = reinterpret_cast<MultiNode*>(smem_raw);
+    float4* slab = reinterpret_cast<float4*>(smem_raw + ((sizeof(MultiNode) * NS + 15) / 16) * 16);
+    const int NU = P.scattering_nu_size, MS = P.scattering_mu_s_size, W = NU * MS;
+    const int x = threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
+    A<F> a(P);
+    F r, mu, mu_s, nu;
+    bool hits;
+    a.TexelToRMuMuSNu((unsigned)min(x, W - 1), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+        const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);                        // multiple_scattering.comp:23-26
+        const F d = F((float)i) * dx;
+        const F r_i = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));      // :35-37
+        const F mu_i = A<F>::ClampCosine((r * mu + d) / r_i);
+        const V tr = a.Transmittance(T, r, mu, d, hits) * dx;                           // :45-48
+        const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);
+        F uvwz[4];
+        a.ScatteringUvwz(r_i, mu_i, F(0.f), F(0.f), hits, uvwz);                        // u_mu, u_r of scattering.h:7-60
+        MultiNode n;
+        F fy, fz;
+        tex_axis(uvwz[2], P.scattering_mu_size, n.y0, n.y1, fy);
+        tex_axis(uvwz[3], P.scattering_r_size, n.z0, n.z1, fz);
+        n.fy = fy.v; n.fz = fz.v;
+        n.d = d.v; n.inv_r = (F(1.f) / r_i).v;
+        n.trw[0] = (tr.x * w).v; n.trw[1] = (tr.y * w).v; n.trw[2] = (tr.z * w).v;
+        nodes[i] = n;
+    }
+    // per-texel constants of the 4-D look-up: the nu slice pair (scattering.h:146-152) ...
+    const F tcx = (nu + F(1.f)) / F(2.f) * F((float)(NU - 1));
+    const F txf = f_floor(tcx);
+    const float ln = (tcx - txf).v;
+    const int tx = min(max((int)txf.v, 0), NU - 1);
+    const int kx0 = tx * MS, kx1 = min(tx + 1, NU - 1) * MS;
+    // ... and the mu_s mapping constants (scattering.h:48-56)
+    const float bot = P.bottom_radius, top = P.top_radius;
+    const float H2 = top * top - bot * bot, b2 = bot * bot, Hh = sqrtf(H2);
+    const float dmin = top - bot, inv_span = 1.f / (Hh - dmin);
+    const float Ac = -2.f * P.mu_s_min * bot / (Hh - dmin), minvA = -1.f / Ac;
+    const float cu1 = 1.f - 1.f / (float)MS, cu0 = 0.5f / (float)MS;
+    const float tmax = __int_as_float(__float_as_int((float)(MS - 1)) - 1);
+    const float rmus = (r * mu_s).v, nuf = nu.v;
+    float ar = 0.f, ag = 0.f, ab = 0.f;
+    const size_t plane = (size_t)P.scattering_mu_size * W;
+    for (int c0 = 0; c0 < NS; c0 += CH) {
+        const int cn = min(CH, NS - c0);
+        __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
+        if (x < W) {
+            for (int e = 0; e < cn; ++e) {        // stage: (mu, r)-bilinear of the density table at this x, per node
+                const MultiNode& n = nodes[c0 + e];
+                const float4 a00 = unpack_half4(__ldg(dens + n.z0 * plane + (size_t)n.y0 * W + x));
+                const float4 a10 = unpack_half4(__ldg(dens + n.z0 * plane + (size_t)n.y1 * W + x));
+                const float4 a01 = unpack_half4(__ldg(dens + n.z1 * plane + (size_t)n.y0 * W + x));
+                const float4 a11 = unpack_half4(__ldg(dens + n.z1 * plane + (size_t)n.y1 * W + x));
+                const float gy = 1.f - n.fy, gz = 1.f - n.fz;
+                float4 v;
+                v.x = fmaf(fmaf(a11.x, n.fy, a01.x * gy), n.fz, fmaf(a10.x, n.fy, a00.x * gy) * gz);
+                v.y = fmaf(fmaf(a11.y, n.fy, a01.y * gy), n.fz, fmaf(a10.y, n.fy, a00.y * gy) * gz);
+                v.z = fmaf(fmaf(a11.z, n.fy, a01.z * gy), n.fz, fmaf(a10.z, n.fy, a00.z * gy) * gz);
+                v.w = 0.f;
+                slab[e * W + x] = v;
+            }
+        }
+        __syncthreads();
+        if (x < W) {
+            for (int e = 0; e < cn; ++e) {
+                const MultiNode& n = nodes[c0 + e];
+                const float mus_i = fminf(fmaxf(fmaf(n.d, nuf, rmus) * n.inv_r, -1.f), 1.f);   // :38
+                const float disc = fmaf(b2, mus_i * mus_i, H2);                        // params.h:108 at r = bottom
+                const float dd = fmaxf(fmaf(-bot, mus_i, sqrtf(fmaxf(disc, 0.f))), 0.f);
+                const float aa = (dd - dmin) * inv_span;
+                const float xx = __fdividef(fmaxf(fmaf(aa, minvA, 1.f), 0.f), 1.f + aa);
+                const float u = fmaf(xx, cu1, cu0);
+                const float t = fminf(fmaxf(fmaf(u, (float)MS, -0.5f), 0.f), tmax);
+                const float tm = __fadd_rd(t, 8388608.f);
+                const int j = __float_as_int(tm) - 0x4B000000;
+                const float fx = t - (tm - 8388608.f);
+                const float4* s = slab + e * W + j;
+                const float4 p00 = s[kx0], p01 = s[kx0 + 1], p10 = s[kx1], p11 = s[kx1 + 1];
+                const float v0r = fmaf(fx, p01.x - p00.x, p00.x), v0g = fmaf(fx, p01.y - p00.y, p00.y), v0b = fmaf(fx, p01.z - p00.z, p00.z);
+                const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z);
+                ar = fmaf(fmaf(ln, v1r - v0r, v0r), n.trw[0], ar);
+                ag = fmaf(fmaf(ln, v1g - v0g, v0g), n.trw[1], ag);
+                ab = fmaf(fmaf(ln, v1b - v0b, v0b), n.trw[2], ab);
+            }
+        }
+    }
+    if (x >= W) return;
+    const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
+    dMS[o] = pack_half4(ar, ag, ab, 0.f);                                               // multiple_scattering.comp:91
+    const F pr = A<F>::RayleighPhase(nu);                                               // :92
+    const float4 s = unpack_half4(S[o]);
+    S[o] = pack_half4((F(ar) / pr + F(s.x)).v, (F(ag) / pr + F(s.y)).v, (F(ab) / pr + F(s.z)).v, __fadd_rn(0.f, s.w));
+}
+
+cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
+    const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
+    if (W > 1024 || c.P.scattering_mu_s_size < 2) return ref::multiple_scattering(c, r0, r1);
+    const int nt = ((W + 31) / 32) * 32;
+    int CH = 3072 / W;
+    CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
+    const size_t smem = ((sizeof(MultiNode) * NS + 15) / 16) * 16 + (size_t)CH * W * sizeof(float4);
+    cudaError_t e = cudaFuncSetAttribute(k_multiple_scattering, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 g(1, c.P.scattering_mu_size, r1 - r0);
+    k_multiple_scattering<<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.scattering_density, c.img.delta_multiple_scattering,
+                                                     c.img.scattering, r0, CH);
+    return cudaGetLastError();
+}
+
+int launches_per_stage(int stage) { return stage == FB_STAGE_SCATTERING_DENSITY ? 2 : 1; }
+
 }  // namespace fast
 }  // namespace fb

@@ -255,12 +255,51 @@ def test_default_dims_against_golden(default_tables):
     print(f"scattering vs fp64 ideal: median {np.median(e):.2e} p99 {np.quantile(e, 0.99):.2e} max {e.max():.2e}")
 
 
-def test_default_dims_fast_matches_reference_family(default_tables, family):
-    """Full default-dims tables of the product kernels vs the contraction-free transcription, texel by texel."""
+def test_default_dims_stagewise_fast_vs_reference_family(family):
+    """Default dims, every stage of the product kernels against the contraction-free transcription ON IDENTICAL INPUTS
+    (the reference family's images are copied over before each stage), every texel of every output image: <= 1e-3."""
+    if family != "fast":
+        pytest.skip("compares the fast family against the reference family once")
+    p = fb.Parameters()
+    R = fb.Atmosphere.allocate(fb.Builder(0, kernels=api.KERNELS_REFERENCE), p)
+    Fp = fb.Atmosphere.allocate(fb.Builder(0, kernels=api.KERNELS_FAST), p)
+    images = list(range(8))
+    f32 = (api.IMAGE_TRANSMITTANCE, api.IMAGE_IRRADIANCE, api.IMAGE_DELTA_IRRADIANCE)
+    for im in images:
+        R.upload(im, np.zeros(R._shape(im), dtype=np.float32 if im in f32 else np.float16))
+
+    def step(stage, order, outs):
+        for im in images:
+            Fp.upload(im, R.download(im))
+        R.run_stage(stage, order=order)
+        Fp.run_stage(stage, order=order)
+        for im in outs:
+            e = (err32 if im in f32 else err16)(Fp.download(im), R.download(im))
+            check(f"stage {stage} order {order} image {im}", e)
+
+    step(api.STAGE_TRANSMITTANCE, 0, [api.IMAGE_TRANSMITTANCE])
+    step(api.STAGE_DIRECT_IRRADIANCE, 0, [api.IMAGE_DELTA_IRRADIANCE])
+    step(api.STAGE_SINGLE_SCATTERING, 0, [api.IMAGE_DELTA_RAYLEIGH, api.IMAGE_DELTA_MIE, api.IMAGE_SCATTERING])
+    step(api.STAGE_CLEAR_IRRADIANCE, 0, [api.IMAGE_IRRADIANCE])
+    for order in (2, 3, 4):
+        step(api.STAGE_SCATTERING_DENSITY, order, [api.IMAGE_SCATTERING_DENSITY])
+        step(api.STAGE_INDIRECT_IRRADIANCE, order - 1, [api.IMAGE_DELTA_IRRADIANCE, api.IMAGE_IRRADIANCE])
+        step(api.STAGE_MULTIPLE_SCATTERING, 0, [api.IMAGE_DELTA_MULTIPLE_SCATTERING, api.IMAGE_SCATTERING])
+
+
+def test_default_dims_end_to_end_fast_vs_reference_family(default_tables, family):
+    """Both families run the whole 4-order pipeline independently.  The fp32 tables must agree to 1e-3 everywhere.
+    For the fp16 scattering table the stage-wise bound cannot hold end to end for ANY two implementations: the
+    reference keeps scattering_density in fp16 where most of it is subnormal (values ~1e-6, 1 ulp = 6e-8 = 6 %), so a
+    single 1-ulp rounding flip there (unavoidable once a sum is associated differently) moves the next
+    multiple-scattering texel by up to ~1 %.  Gate: >= 99.99 % of texels within 1e-3, none beyond 2e-2."""
     if family != "fast":
         pytest.skip("compares the fast family against the reference family once")
     b = fb.Builder(0, kernels=api.KERNELS_REFERENCE)
     T, S, E = fb.precompute_host(b, fb.Parameters())
     check("transmittance fast-vs-reference", err32(default_tables["transmittance"], T))
     check("irradiance fast-vs-reference", err32(default_tables["irradiance"], E))
-    check("scattering fast-vs-reference", err16(default_tables["scattering"], S))
+    e = err16(default_tables["scattering"], S)
+    frac = float((e > RTOL).mean())
+    print(f"scattering fast-vs-reference end to end: max {e.max():.3e}, fraction beyond 1e-3: {frac:.2e}")
+    assert frac <= 1e-4 and e.max() <= 2e-2
