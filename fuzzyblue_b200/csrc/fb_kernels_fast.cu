@@ -78,27 +78,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 //                    lane's register-resident weights; the phi-sum is a 5-step __shfl_xor tree.
 // ---------------------------------------------------------------------------------------------
 constexpr int DL = 16;   // theta samples, scattering_density.comp:34
+// cos / sin of theta_l = (l + 0.5) * pi / 16 as literals: inside the unrolled theta loop they become FFMA immediates
+// (only used where a 1-ulp difference from the host cosf() table is harmless; the exact paths take fb::Trig).
+__device__ constexpr float CT16[DL] = {0.99518472f, 0.956940353f, 0.881921291f, 0.773010433f, 0.634393275f, 0.471396744f, 0.290284663f, 0.0980171412f, -0.0980171412f, -0.290284663f, -0.471396744f, -0.634393275f, -0.773010433f, -0.881921291f, -0.956940353f, -0.99518472f};
+__device__ constexpr float ST16[DL] = {0.0980171412f, 0.290284663f, 0.471396744f, 0.634393275f, 0.773010433f, 0.881921291f, 0.956940353f, 0.99518472f, 0.99518472f, 0.956940353f, 0.881921291f, 0.773010433f, 0.634393275f, 0.471396744f, 0.290284663f, 0.0980171412f};
 
-struct DensityDims {
-    int nu, ms_tile, tiles, T;   // T = ms_tile * nu texels per CTA (<= 256)
+// Texels per CTA are a compile-time constant so that every table offset inside the unrolled theta loop is an
+// immediate: 256 texels at order >= 3 (one look-up table), 128 at order 2 (Rayleigh + Mie tables): 64 KiB either way.
+template <bool ORDER2> struct DensityCfg {
+    static constexpr int E = ORDER2 ? 2 : 1;          // float4 per table entry
+    static constexpr int T = ORDER2 ? 128 : 256;      // texels per CTA = ms_tile * nu
+    static constexpr int NWARPS = 8;
 };
-static inline DensityDims density_dims(const FbParams& P) {
+struct DensityDims {
+    int nu, ms_tile, tiles;
+};
+static inline bool density_supported(const FbParams& P) {
+    const int nu = P.scattering_nu_size;
+    return nu >= 2 && nu <= 128 && (nu & (nu - 1)) == 0 && P.irradiance_mu_s_size <= 1024;
+}
+static inline DensityDims density_dims(const FbParams& P, int T) {
     DensityDims d;
     d.nu = P.scattering_nu_size;
-    int want = 256 / d.nu;
-    if (want < 1) want = 1;
-    d.ms_tile = P.scattering_mu_s_size < want ? P.scattering_mu_s_size : want;
+    d.ms_tile = T / d.nu;
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
-    d.T = d.ms_tile * d.nu;
     return d;
 }
-// floats of scratch: table [R][tiles][DL][T][E] float4  +  ground [R][DL][2] float4
+// scratch: table [R][tiles][DL][T][E] float4 (sized for the larger, order-2 layout) + ground [R][DL][2] float4
 static inline size_t density_tab_float4(const FbParams& P) {
-    DensityDims d = density_dims(P);
-    return (size_t)P.scattering_r_size * d.tiles * DL * d.T * 2;
+    DensityDims d = density_dims(P, DensityCfg<true>::T);
+    return (size_t)P.scattering_r_size * d.tiles * DL * DensityCfg<true>::T * DensityCfg<true>::E;
 }
 
 size_t scratch_bytes(const FbParams& P) {
+    if (!density_supported(P)) return 0;
     return (density_tab_float4(P) + (size_t)P.scattering_r_size * DL * 2) * sizeof(float4);
 }
 
@@ -106,7 +119,7 @@ template <bool ORDER2>
 __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
                                                       Tex3 A0, Tex3 A1, DensityDims dd, float4* __restrict__ tab,
                                                       float4* __restrict__ gnd, int r0) {
-    constexpr int E = ORDER2 ? 2 : 1;
+    constexpr int E = DensityCfg<ORDER2>::E, TT = DensityCfg<ORDER2>::T;
     const int l = blockIdx.y, z = r0 + blockIdx.z;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
     const F nn = F((float)dd.nu);
     const F ux = (F((float)k) + uvwz[1]) / nn;                                        // scattering.h:149
     const int tile = ms / dd.ms_tile, msl = ms % dd.ms_tile;
-    const size_t o = ((((size_t)z * dd.tiles + tile) * DL + l) * dd.T + (size_t)msl * dd.nu + k) * E;
+    const size_t o = ((((size_t)z * dd.tiles + tile) * DL + l) * TT + (size_t)msl * dd.nu + k) * E;
     V4<F> s0 = sample<F>(A0, ux, uvwz[2], uvwz[3]);
     tab[o] = make_float4(s0.x.v, s0.y.v, s0.z.v, 0.f);
     if (ORDER2) {
@@ -137,28 +150,49 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
             F dg = a.DistanceToBottom(r, ct);
             V tgr = a.Transmittance(T, r, ct, dg, true);
             V G = tgr * V(P.ground_albedo) * (F(1.f) / F(FB_PI_F));
-            // |zenith*r + w_i*dg| does not depend on phi: (st*dg)^2 + (r + ct*dg)^2
+            // ground_normal = normalize(zenith*r + w_i*dg); its length does not depend on phi:
+            // (st*dg)^2 + (r + ct*dg)^2, so dot(normal, w_s) = q*(st*dg/len) + mu_s*((r + ct*dg)/len)
+            // with q = sx cos(phi) + sy sin(phi)
             F vx = st * dg, vz = r + ct * dg;
             F len = f_sqrt(vx * vx + vz * vz);
-            g0 = make_float4(1.f, (dg / len).v, (vz / len).v, 0.f);
-            g1 = make_float4(G.x.v, G.y.v, G.z.v, 0.f);
+            g0 = make_float4(G.x.v, G.y.v, G.z.v, (vx / len).v);
+            g1 = make_float4((vz / len).v, 1.f, 0.f, 0.f);
         }
         gnd[((size_t)z * DL + l) * 2] = g0;
         gnd[((size_t)z * DL + l) * 2 + 1] = g1;
     }
 }
 
-template <bool ORDER2, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, ORDER2 ? 1 : 2)
+template <int OFF> __device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; callers guarantee a normal, positive x
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int OFF> __device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+template <bool ORDER2>
+__global__ void __launch_bounds__(256, 2)
 k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float4* __restrict__ tabG,
-               const float4* __restrict__ gndG, const float4* __restrict__ dE_row0, uint2* __restrict__ out, int r0) {
-    constexpr int E = ORDER2 ? 2 : 1;
+               const float4* __restrict__ gndG, const float4* __restrict__ dE_row0, uint2* __restrict__ out, int r0,
+               uint32_t magic_tab, uint32_t magic_row) {
+    typedef DensityCfg<ORDER2> C;
+    constexpr int E = C::E, TT = C::T, NWARPS = C::NWARPS;
+    constexpr uint32_t L_STRIDE = TT * E * sizeof(float4);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [table: DL*T*E float4][geo: T float4][outS: T float4][Wt: DL*32 float4][gnd: DL*2 float4][Erow: n float4][mbar]
+    // [table: DL*TT*E float4][geo: TT float4][outS: TT float4][Wt: DL*32 float4][gnd: DL*2 float4][Erow: n float4][mbar]
     float4* tabS = reinterpret_cast<float4*>(smem_raw);
-    float4* geoS = tabS + (size_t)DL * dd.T * E;
-    float4* outS = geoS + dd.T;
-    float4* WtS = outS + dd.T;
+    float4* geoS = tabS + DL * TT * E;
+    float4* outS = geoS + TT;
+    float4* WtS = outS + TT;
     float4* gndS = WtS + DL * 32;
     float4* ErowS = gndS + DL * 2;
     uint64_t* bar = reinterpret_cast<uint64_t*>(ErowS + P.irradiance_mu_s_size);
@@ -166,22 +200,22 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    const uint32_t tab_bytes = (uint32_t)(DL * dd.T * E * sizeof(float4));
+    constexpr uint32_t tab_bytes = DL * L_STRIDE;
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, tab_bytes);
-        tma_bulk_g2s(tabS, tabG + ((size_t)z * dd.tiles + tile) * DL * dd.T * E, tab_bytes, bar);
+        tma_bulk_g2s(tabS, tabG + ((size_t)z * dd.tiles + tile) * DL * TT * E, tab_bytes, bar);
     }
 
     A<F> a(P);
     // ---- texel geometry, exact (scattering_density.comp:28-32) ------------------------------------------
     F r, mu;
-    for (int t = tid; t < dd.T; t += NWARPS * 32) {
+    for (int t = tid; t < TT; t += NWARPS * 32) {
         const int nui = t / dd.ms_tile, msl = t % dd.ms_tile;
         const int ms = tile * dd.ms_tile + msl;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         if (ms < P.scattering_mu_s_size) {
             F mu_s, nu;
             bool hu;
@@ -219,24 +253,21 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     for (int e = tid; e < P.irradiance_mu_s_size; e += NWARPS * 32) ErowS[e] = __ldg(dE_row0 + e);
     __syncthreads();
 
-    // ---- per-lane constants: direction components and weights of phi sample `lane` ------------------------
-    float wx[DL], wy[DL], Wr[DL], Wg[DL], Wb[DL];
-    uint32_t gmask = 0;
+    // ---- per-lane constants: the weights of phi sample `lane` for the 16 theta rows (registers) ------------
+    float Wr[DL], Wg[DL], Wb[DL];
 #pragma unroll
     for (int l = 0; l < DL; ++l) {
-        wx[l] = __fmul_rn(tg.cp32[lane], tg.st16[l]);
-        wy[l] = __fmul_rn(tg.sp32[lane], tg.st16[l]);
-        float4 w = WtS[l * 32 + lane];
+        const float4 w = WtS[l * 32 + lane];
         Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
-        if (gndS[l * 2].x != 0.f) gmask |= 1u << l;
     }
+    uint32_t gmask = 0;
+    for (int l = 0; l < DL; ++l)
+        if (gndS[l * 2 + 1].y != 0.f) gmask |= 1u << l;
+    const float cp = tg.cp32[lane], sp = tg.sp32[lane];
     const float hn = 0.5f * (float)(dd.nu - 1);
-    const float tmax = __int_as_float(__float_as_int((float)(dd.nu - 1)) - 1);   // largest float below nu-1
-    const float MAGIC = 8388608.f;
-    const int nE = P.irradiance_mu_s_size;
-    // GetIrradiance at r = bottom: v lands on row 0; u*N - 0.5 = (0.5/N + x(1 - 1/N))*N - 0.5 with x = mu_s*0.5 + 0.5
-    const float e_c1 = 0.5f * (float)(nE - 1), e_c0 = 0.5f * (float)(nE - 1);
-    const float e_max = __int_as_float(__float_as_int((float)(nE - 1)) - 1);
+    const float MAGIC = 8388608.f;   // 2^23: x + MAGIC rounded down leaves floor(x) in the low mantissa bits
+    // GetIrradiance at r = bottom lands on row 0: u*N - 0.5 = (mu_s*0.5 + 0.5)*(N - 1)
+    const float e_c = 0.5f * (float)(P.irradiance_mu_s_size - 1);
     float kR = 0.f, kMR = 0.f, g2p1 = 0.f, m2g = 0.f;
     if (ORDER2) {
         const float g = P.mie_phase_function_g;
@@ -246,52 +277,76 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         g2p1 = 1.f + g * g;
         m2g = -2.f * g;
     }
+    // (bits(x + MAGIC) << 4) == 0xB0000000 + 16*floor(x)  (mod 2^32): fold the constant into the base address.
+    // The constants arrive as kernel arguments on purpose: as literals ptxas splits them off the base again and
+    // spends an extra IADD3 per load.
+    constexpr int GND_OFF = (DL * TT * E + 2 * TT + DL * 32) * (int)sizeof(float4);
+    constexpr int EROW_OFF = GND_OFF + DL * 2 * (int)sizeof(float4);
+    uint32_t sbase = smem_u32(smem_raw);
+    asm volatile("" : "+r"(sbase));           // one register for every region; offsets below are immediates
+    const uint32_t tab_base = sbase - magic_tab;
+    const uint32_t erow_t = sbase - magic_row;
 
     mbar_wait(bar, 0);
 
     // ---- one warp per texel, lane = phi sample -------------------------------------------------------------
-    for (int t = warp; t < dd.T; t += NWARPS) {
+    for (int t = warp; t < TT; t += NWARPS) {
         const float4 geo = geoS[t];
-        const float sx = geo.x, sy = geo.y, mus = geo.z;
-        const float4* row_t = tabS + __float_as_int(geo.w);
-        float ar = 0.f, ag = 0.f, ab = 0.f;
-#pragma unroll
-        for (int l = 0; l < DL; ++l) {
-            const float h = fmaf(sx, wx[l], sy * wy[l]);
-            const float nu1 = fmaf(mus, tg.ct16[l], h);
-            float tcx = fminf(fmaxf(fmaf(nu1, hn, hn), 0.f), tmax);              // scattering.h:146
-            const float tm = __fadd_rd(tcx, MAGIC);
-            const int k = __float_as_int(tm) - 0x4B000000;                        // floor(tcx)
-            const float f = tcx - (tm - MAGIC);
-            const float4* p = row_t + (size_t)l * dd.T * E + k * E;
-            float Lr, Lg, Lb;
-            if (ORDER2) {
-                const float4 r0v = p[0], m0v = p[1], r1v = p[2], m1v = p[3];
-                const float pr = fmaf(nu1 * kR, nu1, kR);                         // util.h:26-29
-                const float base = fmaf(m2g, nu1, g2p1);
-                const float rs = rsqrtf(base);
-                const float pm = pr * kMR * (rs * rs * rs);                       // util.h:31-34, x^-1.5 = rsqrt(x)^3
-                const float rr = fmaf(f, r1v.x - r0v.x, r0v.x), rg = fmaf(f, r1v.y - r0v.y, r0v.y), rb = fmaf(f, r1v.z - r0v.z, r0v.z);
-                const float mr = fmaf(f, m1v.x - m0v.x, m0v.x), mg = fmaf(f, m1v.y - m0v.y, m0v.y), mb = fmaf(f, m1v.z - m0v.z, m0v.z);
-                Lr = fmaf(mr, pm, rr * pr); Lg = fmaf(mg, pm, rg * pr); Lb = fmaf(mb, pm, rb * pr);
-            } else {
-                const float4 v0 = p[0], v1 = p[1];
-                Lr = fmaf(f, v1.x - v0.x, v0.x); Lg = fmaf(f, v1.y - v0.y, v0.y); Lb = fmaf(f, v1.z - v0.z, v0.z);
-            }
-            if (gmask & (1u << l)) {                                              // warp-uniform
-                const float4 g0 = gndS[l * 2], G = gndS[l * 2 + 1];
-                const float musg = fmaf(h, g0.y, mus * g0.z);                     // dot(ground_normal, omega_s)
-                float te = fminf(fmaxf(fmaf(musg, e_c1, e_c0), 0.f), e_max);      // irradiance.h:20-30 at r = bottom
-                const float em = __fadd_rd(te, MAGIC);
-                const int j = __float_as_int(em) - 0x4B000000;
-                const float fe = te - (em - MAGIC);
-                const float4 e0 = ErowS[j], e1 = ErowS[j + 1];
-                Lr = fmaf(G.x, fmaf(fe, e1.x - e0.x, e0.x), Lr);
-                Lg = fmaf(G.y, fmaf(fe, e1.y - e0.y, e0.y), Lg);
-                Lb = fmaf(G.z, fmaf(fe, e1.z - e0.z, e0.z), Lb);
-            }
-            ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);
+        if (__float_as_int(geo.w) < 0) continue;                                  // padding texel of a partial tile
+        // w_s . w_i = sin(theta_l) * q + mu_s * cos(theta_l) with q = sx cos(phi) + sy sin(phi) per (texel, lane).
+        // |w_s . w_i| <= sqrt(q^2 + mu_s^2) for every theta; pull (q, mu_s) inside the unit disc by a hair so that
+        // neither the nu look-up below nor the ground look-up can step outside its table row — no per-sample clamps.
+        float q = fmaf(geo.x, cp, geo.y * sp), mus = geo.z;
+        {
+            const float n2 = fmaf(q, q, mus * mus);
+            const float sc = n2 > 0.999998f ? 0.999999f * rsqrt_fast(n2) : 1.f;
+            q *= sc; mus *= sc;
         }
+        const uint32_t row_t = tab_base + (uint32_t)__float_as_int(geo.w) * (uint32_t)sizeof(float4);
+        float ar = 0.f, ag = 0.f, ab = 0.f;
+#define FB_DENSITY_STEP(l)                                                                                              \
+        {                                                                                                               \
+            const float nu1 = fmaf(mus, CT16[l], q * ST16[l]);                                                          \
+            const float tcx = fmaf(nu1, hn, hn);                                  /* scattering.h:146, in [0, nu-1) */  \
+            const float tm = __fadd_rd(tcx, MAGIC);                                                                     \
+            const float f = tcx - (tm - MAGIC);                                                                         \
+            const uint32_t addr = row_t + (__float_as_uint(tm) << (ORDER2 ? 5 : 4));                                    \
+            float Lr, Lg, Lb;                                                                                           \
+            if (ORDER2) {                                                                                               \
+                const float4 r0v = lds128<(l) * L_STRIDE>(addr), m0v = lds128<(l) * L_STRIDE + 16>(addr);               \
+                const float4 r1v = lds128<(l) * L_STRIDE + 32>(addr), m1v = lds128<(l) * L_STRIDE + 48>(addr);          \
+                const float pr = fmaf(nu1 * kR, nu1, kR);                         /* util.h:26-29 */                    \
+                const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));                                                          \
+                const float pm = pr * kMR * (rs * rs * rs);                       /* util.h:31-34: x^-1.5 = rsqrt^3 */  \
+                const float rr = fmaf(f, r1v.x - r0v.x, r0v.x), rg = fmaf(f, r1v.y - r0v.y, r0v.y),                     \
+                            rb = fmaf(f, r1v.z - r0v.z, r0v.z);                                                         \
+                const float mr = fmaf(f, m1v.x - m0v.x, m0v.x), mg = fmaf(f, m1v.y - m0v.y, m0v.y),                     \
+                            mb = fmaf(f, m1v.z - m0v.z, m0v.z);                                                         \
+                Lr = fmaf(mr, pm, rr * pr); Lg = fmaf(mg, pm, rg * pr); Lb = fmaf(mb, pm, rb * pr);                     \
+            } else {                                                                                                    \
+                const float4 v0 = lds128<(l) * L_STRIDE>(addr), v1 = lds128<(l) * L_STRIDE + 16>(addr);                 \
+                Lr = fmaf(f, v1.x - v0.x, v0.x); Lg = fmaf(f, v1.y - v0.y, v0.y); Lb = fmaf(f, v1.z - v0.z, v0.z);      \
+            }                                                                                                           \
+            if (gmask & (1u << (l))) {                                            /* warp-uniform */                    \
+                const float4 G = lds128<GND_OFF + (l) * 32>(sbase);                          /* (G.rgb, n_x) */                    \
+                const float gz = lds32<GND_OFF + (l) * 32 + 16>(sbase);                                                        \
+                const float musg = fmaf(q, G.w, mus * gz);                        /* dot(ground_normal, omega_s) */     \
+                const float te = fmaf(musg, e_c, e_c);                            /* irradiance.h:20-30, r = bottom */  \
+                const float em = __fadd_rd(te, MAGIC);                                                                  \
+                const float fe = te - (em - MAGIC);                                                                     \
+                const uint32_t ea = erow_t + (__float_as_uint(em) << 4);                                             \
+                const float4 e0 = lds128<EROW_OFF>(ea), e1 = lds128<EROW_OFF + 16>(ea);                                                   \
+                Lr = fmaf(G.x, fmaf(fe, e1.x - e0.x, e0.x), Lr);                                                        \
+                Lg = fmaf(G.y, fmaf(fe, e1.y - e0.y, e0.y), Lg);                                                        \
+                Lb = fmaf(G.z, fmaf(fe, e1.z - e0.z, e0.z), Lb);                                                        \
+            }                                                                                                           \
+            ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);                               \
+        }
+        FB_DENSITY_STEP(0) FB_DENSITY_STEP(1) FB_DENSITY_STEP(2) FB_DENSITY_STEP(3)
+        FB_DENSITY_STEP(4) FB_DENSITY_STEP(5) FB_DENSITY_STEP(6) FB_DENSITY_STEP(7)
+        FB_DENSITY_STEP(8) FB_DENSITY_STEP(9) FB_DENSITY_STEP(10) FB_DENSITY_STEP(11)
+        FB_DENSITY_STEP(12) FB_DENSITY_STEP(13) FB_DENSITY_STEP(14) FB_DENSITY_STEP(15)
+#undef FB_DENSITY_STEP
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
             ar += __shfl_xor_sync(0xffffffffu, ar, s);
@@ -301,7 +356,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         if (lane == 0) outS[t] = make_float4(ar, ag, ab, 0.f);
     }
     __syncthreads();
-    for (int t = tid; t < dd.T; t += NWARPS * 32) {
+    for (int t = tid; t < TT; t += NWARPS * 32) {
         const int nui = t / dd.ms_tile, ms = tile * dd.ms_tile + t % dd.ms_tile;
         if (ms < P.scattering_mu_s_size) {
             const float4 v = outS[t];
@@ -310,37 +365,37 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     }
 }
 
-static size_t density_smem(const FbParams& P, const DensityDims& d, bool order2) {
-    return ((size_t)DL * d.T * (order2 ? 2 : 1) + 2 * d.T + DL * 32 + DL * 2 + P.irradiance_mu_s_size) * sizeof(float4) + 16;
+template <bool ORDER2> static size_t density_smem(const FbParams& P) {
+    typedef DensityCfg<ORDER2> C;
+    return ((size_t)DL * C::T * C::E + 2 * C::T + DL * 32 + DL * 2 + P.irradiance_mu_s_size) * sizeof(float4) + 16;
 }
 
-cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1) {
+template <bool ORDER2>
+static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, int r1) {
+    typedef DensityCfg<ORDER2> C;
     const FbParams& P = c.P;
-    DensityDims d = density_dims(P);
-    const bool o2 = order == 2;
-    const size_t smem = density_smem(P, d, o2);
-    if (P.scattering_nu_size < 2 || smem > 220 * 1024 || !c.img.scratch) return ref::scattering_density(c, order, r0, r1);
+    const DensityDims d = density_dims(P, C::T);
+    const size_t smem = density_smem<ORDER2>(P);
     float4* tab = reinterpret_cast<float4*>(c.img.scratch);
     float4* gnd = tab + density_tab_float4(P);
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     dim3 gp((W + 255) / 256, DL, r1 - r0);
     dim3 gm(d.tiles, P.scattering_mu_size, r1 - r0);
-    cudaError_t e;
-    if (o2) {
-        k_density_prep<true><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), d, tab, gnd, r0);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_density_main<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_density_main<true, 16><<<gm, 16 * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance, c.img.scattering_density, r0);
-    } else {
-        k_density_prep<false><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), texS(c, c.img.delta_multiple_scattering),
-                                                         texS(c, c.img.delta_multiple_scattering), d, tab, gnd, r0);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_density_main<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_density_main<false, 8><<<gm, 8 * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance, c.img.scattering_density, r0);
-    }
+    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, gnd, r0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance,
+                                                                  c.img.scattering_density, r0,
+                                                                  ORDER2 ? 0x60000000u : 0xB0000000u, 0xB0000000u);
     return cudaGetLastError();
+}
+
+cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1) {
+    if (!density_supported(c.P) || !c.img.scratch) return ref::scattering_density(c, order, r0, r1);
+    if (order == 2) return density_launch<true>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1);
+    return density_launch<false>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1);
 }
 
 // ---------------------------------------------------------------------------------------------

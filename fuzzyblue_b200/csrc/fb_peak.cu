@@ -21,13 +21,19 @@ __global__ void __launch_bounds__(256) k_peak_fma(float* out, float a, float b) 
     if (s == 123.456f) out[0] = s;   // never true; keeps the chains alive
 }
 
+__device__ __forceinline__ float rsq(float x) {
+    float y;
+    asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int ITERS>
 __global__ void __launch_bounds__(256) k_peak_sfu(float* out, float seed) {
     float x0 = seed + threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
 #pragma unroll 8
     for (int i = 0; i < ITERS; ++i) {
-        x0 = __frsqrt_rn(x0); x1 = __frsqrt_rn(x1); x2 = __frsqrt_rn(x2); x3 = __frsqrt_rn(x3);
-        x4 = __frsqrt_rn(x4); x5 = __frsqrt_rn(x5); x6 = __frsqrt_rn(x6); x7 = __frsqrt_rn(x7);
+        x0 = rsq(x0); x1 = rsq(x1); x2 = rsq(x2); x3 = rsq(x3);
+        x4 = rsq(x4); x5 = rsq(x5); x6 = rsq(x6); x7 = rsq(x7);
     }
     float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 123.456f) out[0] = s;
