@@ -1,0 +1,191 @@
+//! Drop-in shim: the six public names of Ralith/fuzzyblue (`src/lib.rs:8-12`) implemented over the C ABI of
+//! `include/fuzzyblue.h`.  A CUDA stream (`*mut c_void`, null = default stream) stands where the reference takes a
+//! `vk::CommandBuffer`; device pointers stand where it returns `vk::Image`s.  The four Vulkan-only fields of
+//! `Parameters` are kept (as plain integers) so struct-update call sites such as `tests/smoke.rs:136-142` compile.
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Rust toolchain); the ABI it binds is exercised by the Python and C++
+//! mirrors in the test-suite.
+use std::os::raw::{c_char, c_int, c_void};
+use std::sync::Arc;
+
+#[allow(non_camel_case_types)]
+pub mod ffi {
+    use super::*;
+    #[repr(C)] #[derive(Copy, Clone, Default)]
+    pub struct FbDensityProfileLayer { pub width: f32, pub exp_term: f32, pub exp_scale: f32, pub linear_term: f32, pub constant_term: f32, pub _pad: [f32; 3] }
+    #[repr(C)] #[derive(Copy, Clone, Default)]
+    pub struct FbDensityProfile { pub layers: [FbDensityProfileLayer; 2] }
+    /// Byte-identical to `ParamsRaw` (src/precompute.rs:937-1033): 320 bytes.
+    #[repr(C)] #[derive(Copy, Clone, Default)]
+    pub struct FbParams {
+        pub solar_irradiance: [f32; 3], pub sun_angular_radius: f32,
+        pub rayleigh_scattering: [f32; 3], pub bottom_radius: f32,
+        pub mie_scattering: [f32; 3], pub top_radius: f32,
+        pub mie_extinction: [f32; 3], pub mie_phase_function_g: f32,
+        pub ground_albedo: [f32; 3], pub mu_s_min: f32,
+        pub absorption_extinction: [f32; 3],
+        pub transmittance_mu_size: i32, pub transmittance_r_size: i32,
+        pub scattering_r_size: i32, pub scattering_mu_size: i32, pub scattering_mu_s_size: i32, pub scattering_nu_size: i32,
+        pub irradiance_mu_s_size: i32, pub irradiance_r_size: i32, pub _pad: i32,
+        pub rayleigh_density: FbDensityProfile, pub mie_density: FbDensityProfile, pub absorption_density: FbDensityProfile,
+    }
+    /// Byte-identical to `DrawParamsRaw` (src/render.rs:254-260): 92 bytes.
+    #[repr(C)] #[derive(Copy, Clone)]
+    pub struct FbDrawParams { pub inverse_viewproj: [[f32; 4]; 4], pub camera_position: [f32; 3], pub _pad: u32, pub sun_direction: [f32; 3] }
+    #[repr(C)] #[derive(Copy, Clone, Default)] pub struct FbExtent2D { pub width: u32, pub height: u32 }
+    #[repr(C)] #[derive(Copy, Clone, Default)] pub struct FbExtent3D { pub width: u32, pub height: u32, pub depth: u32 }
+    pub enum FbBuilder {} pub enum FbPending {} pub enum FbAtmosphere {} pub enum FbRenderer {}
+    extern "C" {
+        pub fn fb_last_error() -> *const c_char;
+        pub fn fb_builder_create(device: c_int, out: *mut *mut FbBuilder) -> c_int;
+        pub fn fb_builder_destroy(b: *mut FbBuilder);
+        pub fn fb_atmosphere_build(b: *mut FbBuilder, p: *const FbParams, order: u32, stream: *mut c_void, out: *mut *mut FbPending) -> c_int;
+        pub fn fb_pending_resubmit(p: *mut FbPending, stream: *mut c_void) -> c_int;
+        pub fn fb_pending_atmosphere(p: *mut FbPending, out: *mut *const FbAtmosphere) -> c_int;
+        pub fn fb_pending_assert_ready(p: *mut FbPending, check: c_int, out: *mut *mut FbAtmosphere) -> c_int;
+        pub fn fb_pending_destroy(p: *mut FbPending);
+        pub fn fb_atmosphere_transmittance(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent2D) -> c_int;
+        pub fn fb_atmosphere_scattering(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent3D) -> c_int;
+        pub fn fb_atmosphere_irradiance(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent2D) -> c_int;
+        pub fn fb_atmosphere_destroy(a: *mut FbAtmosphere);
+        pub fn fb_renderer_create(b: *mut FbBuilder, out: *mut *mut FbRenderer) -> c_int;
+        pub fn fb_renderer_destroy(r: *mut FbRenderer);
+        pub fn fb_renderer_draw(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, depth: *const f32,
+                                color: *mut f32, transmittance: *mut f32, w: u32, h: u32, stream: *mut c_void) -> c_int;
+    }
+}
+
+fn check(status: c_int) {
+    // the reference panics through .unwrap() on every Vulkan error (e.g. src/precompute.rs:83,98,529)
+    if status != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(ffi::fb_last_error()) }.to_string_lossy().into_owned();
+        panic!("fuzzyblue_b200: status {}: {}", status, msg);
+    }
+}
+
+/// src/precompute.rs:660-666
+#[derive(Debug, Copy, Clone, Default)]
+pub struct DensityProfileLayer { pub width: f32, pub exp_term: f32, pub exp_scale: f32, pub linear_term: f32, pub constant_term: f32 }
+/// src/precompute.rs:674-676
+#[derive(Debug, Copy, Clone, Default)]
+pub struct DensityProfile { pub layers: [DensityProfileLayer; 2] }
+
+/// src/precompute.rs:690-769.  `usage`, `dst_stage_mask`, `dst_access_mask`, `layout` are accepted and ignored.
+#[derive(Debug, Clone)]
+pub struct Parameters {
+    pub usage: u32, pub dst_stage_mask: u32, pub dst_access_mask: u32, pub layout: i32,
+    pub order: u32,
+    pub transmittance_mu_size: u32, pub transmittance_r_size: u32,
+    pub scattering_r_size: u32, pub scattering_mu_size: u32, pub scattering_mu_s_size: u32, pub scattering_nu_size: u32,
+    pub irradiance_mu_s_size: u32, pub irradiance_r_size: u32,
+    pub solar_irradiance: [f32; 3], pub sun_angular_radius: f32, pub bottom_radius: f32, pub top_radius: f32,
+    pub rayleigh_density: DensityProfile, pub rayleigh_scattering: [f32; 3],
+    pub mie_density: DensityProfile, pub mie_scattering: [f32; 3], pub mie_extinction: [f32; 3], pub mie_phase_function_g: f32,
+    pub absorbtion_density: DensityProfile, pub absorbtion_extinction: [f32; 3],
+    pub ground_albedo: [f32; 3], pub mu_s_min: f32,
+}
+
+impl Default for Parameters {
+    /// src/precompute.rs:849-935 (Earth)
+    fn default() -> Self {
+        let exp = |scale: f32| DensityProfile { layers: [DensityProfileLayer::default(),
+            DensityProfileLayer { width: 0.0, exp_term: 1.0, exp_scale: scale, linear_term: 0.0, constant_term: 0.0 }] };
+        Self {
+            usage: 0, dst_stage_mask: 0x80, dst_access_mask: 0x20, layout: 5, order: 4,
+            transmittance_mu_size: 256, transmittance_r_size: 64,
+            scattering_r_size: 32, scattering_mu_size: 128, scattering_mu_s_size: 32, scattering_nu_size: 8,
+            irradiance_mu_s_size: 64, irradiance_r_size: 16,
+            solar_irradiance: [1.474, 1.850, 1.91198], sun_angular_radius: 0.004675, bottom_radius: 6360.0, top_radius: 6420.0,
+            rayleigh_density: exp(-0.125), rayleigh_scattering: [0.005802, 0.013558, 0.033100],
+            mie_density: exp(-0.833333), mie_scattering: [0.003996; 3], mie_extinction: [0.004440; 3], mie_phase_function_g: 0.8,
+            absorbtion_density: DensityProfile { layers: [
+                DensityProfileLayer { width: 25.0, exp_term: 0.0, exp_scale: 0.0, linear_term: 0.066667, constant_term: -0.666667 },
+                DensityProfileLayer { width: 0.0, exp_term: 0.0, exp_scale: 0.0, linear_term: -0.066667, constant_term: 2.666667 }] },
+            absorbtion_extinction: [6.5e-4, 1.881e-3, 8.5e-5], ground_albedo: [0.1; 3], mu_s_min: -0.207912,
+        }
+    }
+}
+
+impl Parameters {
+    /// src/precompute.rs:771-793
+    pub fn transmittance_extent(&self) -> (u32, u32) { (self.transmittance_mu_size, self.transmittance_r_size) }
+    pub fn irradiance_extent(&self) -> (u32, u32) { (self.irradiance_mu_s_size, self.irradiance_r_size) }
+    pub fn scattering_extent(&self) -> (u32, u32, u32) { (self.scattering_nu_size * self.scattering_mu_s_size, self.scattering_mu_size, self.scattering_r_size) }
+    /// ParamsRaw::new, src/precompute.rs:964-991
+    fn raw(&self) -> ffi::FbParams {
+        let prof = |p: &DensityProfile| { let mut o = ffi::FbDensityProfile::default(); for i in 0..2 { let l = &p.layers[i];
+            o.layers[i] = ffi::FbDensityProfileLayer { width: l.width, exp_term: l.exp_term, exp_scale: l.exp_scale, linear_term: l.linear_term, constant_term: l.constant_term, _pad: [0.0; 3] }; } o };
+        ffi::FbParams {
+            solar_irradiance: self.solar_irradiance, sun_angular_radius: self.sun_angular_radius,
+            rayleigh_scattering: self.rayleigh_scattering, bottom_radius: self.bottom_radius,
+            mie_scattering: self.mie_scattering, top_radius: self.top_radius,
+            mie_extinction: self.mie_extinction, mie_phase_function_g: self.mie_phase_function_g,
+            ground_albedo: self.ground_albedo, mu_s_min: self.mu_s_min, absorption_extinction: self.absorbtion_extinction,
+            transmittance_mu_size: self.transmittance_mu_size as i32, transmittance_r_size: self.transmittance_r_size as i32,
+            scattering_r_size: self.scattering_r_size as i32, scattering_mu_size: self.scattering_mu_size as i32,
+            scattering_mu_s_size: self.scattering_mu_s_size as i32, scattering_nu_size: self.scattering_nu_size as i32,
+            irradiance_mu_s_size: self.irradiance_mu_s_size as i32, irradiance_r_size: self.irradiance_r_size as i32, _pad: 0,
+            rayleigh_density: prof(&self.rayleigh_density), mie_density: prof(&self.mie_density), absorption_density: prof(&self.absorbtion_density),
+        }
+    }
+}
+
+/// `Builder::new` (src/precompute.rs:61-68): the Vulkan instance/device/cache/queue arguments collapse to a CUDA ordinal.
+pub struct Builder { raw: *mut ffi::FbBuilder }
+impl Builder {
+    pub fn new(device: i32) -> Self { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::fb_builder_create(device, &mut raw) }); Self { raw } }
+}
+impl Drop for Builder { fn drop(&mut self) { unsafe { ffi::fb_builder_destroy(self.raw) } } }
+
+/// src/precompute.rs:1036-1043
+pub struct Atmosphere { _builder: Arc<Builder>, raw: *const ffi::FbAtmosphere, owned: bool }
+impl Atmosphere {
+    /// `Atmosphere::build(builder, cmd, &params)` (src/precompute.rs:1077-1081): enqueue on `stream`, return at once.
+    pub unsafe fn build(builder: Arc<Builder>, stream: *mut c_void, params: &Parameters) -> PendingAtmosphere {
+        let mut raw = std::ptr::null_mut();
+        check(ffi::fb_atmosphere_build(builder.raw, &params.raw(), params.order, stream, &mut raw));
+        PendingAtmosphere { builder, raw }
+    }
+    /// Device pointers to the linear tables (layout: include/fuzzyblue.h) — the `vk::Image` getters of :2075-2101.
+    pub fn transmittance(&self) -> *const c_void { let mut p = std::ptr::null(); check(unsafe { ffi::fb_atmosphere_transmittance(self.raw, &mut p, std::ptr::null_mut()) }); p }
+    pub fn transmittance_extent(&self) -> (u32, u32) { let mut e = ffi::FbExtent2D::default(); check(unsafe { ffi::fb_atmosphere_transmittance(self.raw, std::ptr::null_mut(), &mut e) }); (e.width, e.height) }
+    pub fn scattering(&self) -> *const c_void { let mut p = std::ptr::null(); check(unsafe { ffi::fb_atmosphere_scattering(self.raw, &mut p, std::ptr::null_mut()) }); p }
+    pub fn scattering_extent(&self) -> (u32, u32, u32) { let mut e = ffi::FbExtent3D::default(); check(unsafe { ffi::fb_atmosphere_scattering(self.raw, std::ptr::null_mut(), &mut e) }); (e.width, e.height, e.depth) }
+    pub fn irradiance(&self) -> *const c_void { let mut p = std::ptr::null(); check(unsafe { ffi::fb_atmosphere_irradiance(self.raw, &mut p, std::ptr::null_mut()) }); p }
+    pub fn irradiance_extent(&self) -> (u32, u32) { let mut e = ffi::FbExtent2D::default(); check(unsafe { ffi::fb_atmosphere_irradiance(self.raw, std::ptr::null_mut(), &mut e) }); (e.width, e.height) }
+}
+impl Drop for Atmosphere { fn drop(&mut self) { if self.owned { unsafe { ffi::fb_atmosphere_destroy(self.raw as *mut _) } } } }
+
+/// src/precompute.rs:2103-2120.  Must outlive the work enqueued by `Atmosphere::build`.
+pub struct PendingAtmosphere { builder: Arc<Builder>, raw: *mut ffi::FbPending }
+impl PendingAtmosphere {
+    /// Queue-family ownership transfer (:2147-2201) has no CUDA analogue.
+    pub unsafe fn acquire_ownership(&self, _stream: *mut c_void, _compute_queue_family: u32, _gfx_queue_family: u32) {}
+    pub unsafe fn atmosphere(&self) -> Atmosphere { let mut a = std::ptr::null(); check(ffi::fb_pending_atmosphere(self.raw, &mut a)); Atmosphere { _builder: self.builder.clone(), raw: a, owned: false } }
+    /// Caller asserts the stream has completed (:2208-2211).
+    pub unsafe fn assert_ready(mut self) -> Atmosphere {
+        let mut a = std::ptr::null_mut(); check(ffi::fb_pending_assert_ready(self.raw, 0, &mut a)); self.raw = std::ptr::null_mut();
+        Atmosphere { _builder: self.builder.clone(), raw: a, owned: true }
+    }
+    /// Re-submit the recorded stream (what benches/precompute.rs:138-148 does with its command buffer).
+    pub unsafe fn resubmit(&self, stream: *mut c_void) { check(ffi::fb_pending_resubmit(self.raw, stream)) }
+}
+impl Drop for PendingAtmosphere { fn drop(&mut self) { if !self.raw.is_null() { unsafe { ffi::fb_pending_destroy(self.raw) } } } }
+
+/// src/render.rs:246-252
+#[derive(Debug, Copy, Clone)]
+pub struct DrawParameters { pub inverse_viewproj: [[f32; 4]; 4], pub camera_position: [f32; 3], pub sun_direction: [f32; 3] }
+
+/// src/render.rs:13-19; render pass / subpass / frame count have no CUDA meaning.
+pub struct Renderer { raw: *mut ffi::FbRenderer, depth: Vec<*const f32> }
+impl Renderer {
+    pub fn new(builder: &Builder, frames: u32) -> Self { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::fb_renderer_create(builder.raw, &mut raw) }); Self { raw, depth: vec![std::ptr::null(); frames as usize] } }
+    /// src/render.rs:194-207: the depth attachment of a frame, here a device pointer to `[h][w]` f32.
+    pub unsafe fn set_depth_buffer(&mut self, frame: u32, depth: *const f32) { self.depth[frame as usize] = depth; }
+    /// src/render.rs:209-236 with the two fragment outputs as explicit `[h][w][4]` f32 device buffers.
+    pub fn draw(&self, stream: *mut c_void, atmosphere: &Atmosphere, frame: u32, params: &DrawParameters, color: *mut f32, transmittance: *mut f32, width: u32, height: u32) {
+        let raw = ffi::FbDrawParams { inverse_viewproj: params.inverse_viewproj, camera_position: params.camera_position, _pad: 0, sun_direction: params.sun_direction };
+        check(unsafe { ffi::fb_renderer_draw(self.raw, atmosphere.raw, &raw, self.depth[frame as usize], color, transmittance, width, height, stream) });
+    }
+}
+impl Drop for Renderer { fn drop(&mut self) { unsafe { ffi::fb_renderer_destroy(self.raw) } } }
