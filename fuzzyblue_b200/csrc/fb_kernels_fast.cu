@@ -84,9 +84,15 @@ __device__ constexpr float CT16[DL] = {0.99518472f, 0.956940353f, 0.881921291f, 
 __device__ constexpr float ST16[DL] = {0.0980171412f, 0.290284663f, 0.471396744f, 0.634393275f, 0.773010433f, 0.881921291f, 0.956940353f, 0.99518472f, 0.99518472f, 0.956940353f, 0.881921291f, 0.773010433f, 0.634393275f, 0.471396744f, 0.290284663f, 0.0980171412f};
 
 // Texels per CTA are a compile-time constant so that every table offset inside the unrolled theta loop is an
-// immediate: 256 texels at order >= 3 (one look-up table), 128 at order 2 (Rayleigh + Mie tables): 64 KiB either way.
+// immediate: 256 texels at order >= 3 (one look-up table), 128 at order 2 (Rayleigh + Mie tables): 96 KiB either way.
+//
+// Table entries are (value, delta-to-next-knot) pairs per channel, so the nu interpolation is one FFMA per channel and
+// a sample reads exactly the 6 (12 at order 2) words it needs: the shared-memory data pipe is the binding unit of this
+// kernel and an LDS costs one wavefront per 4 bytes per lane whatever the address pattern (tools/lds_bench.cu).
+//   order >= 3 entry, 24 B:  [R.r dR.r | R.g dR.g | R.b dR.b]                              3 x LDS.64
+//   order 2    entry, 48 B:  [R.r dR.r R.g dR.g | R.b dR.b M.r dM.r | M.g dM.g M.b dM.b]   3 x LDS.128
 template <bool ORDER2> struct DensityCfg {
-    static constexpr int E = ORDER2 ? 2 : 1;          // float4 per table entry
+    static constexpr int ENT = ORDER2 ? 12 : 6;       // floats per table entry
     static constexpr int T = ORDER2 ? 128 : 256;      // texels per CTA = ms_tile * nu
     static constexpr int NWARPS = 8;
 };
@@ -95,7 +101,7 @@ struct DensityDims {
 };
 static inline bool density_supported(const FbParams& P) {
     const int nu = P.scattering_nu_size;
-    return nu >= 2 && nu <= 128 && (nu & (nu - 1)) == 0 && P.irradiance_mu_s_size <= 1024;
+    return nu >= 2 && nu <= 128 && (nu & (nu - 1)) == 0 && P.irradiance_mu_s_size <= 512;
 }
 static inline DensityDims density_dims(const FbParams& P, int T) {
     DensityDims d;
@@ -104,22 +110,22 @@ static inline DensityDims density_dims(const FbParams& P, int T) {
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
     return d;
 }
-// scratch: table [R][tiles][DL][T][E] float4 (sized for the larger, order-2 layout) + ground [R][DL][2] float4
-static inline size_t density_tab_float4(const FbParams& P) {
+// scratch: table [R][tiles][DL][T][ENT] floats (sized for the order-2 layout, the larger one) + ground [R][DL][2] float4
+static inline size_t density_tab_floats(const FbParams& P) {
     DensityDims d = density_dims(P, DensityCfg<true>::T);
-    return (size_t)P.scattering_r_size * d.tiles * DL * DensityCfg<true>::T * DensityCfg<true>::E;
+    return (size_t)P.scattering_r_size * d.tiles * DL * DensityCfg<true>::T * DensityCfg<true>::ENT;
 }
 
 size_t scratch_bytes(const FbParams& P) {
     if (!density_supported(P)) return 0;
-    return (density_tab_float4(P) + (size_t)P.scattering_r_size * DL * 2) * sizeof(float4);
+    return density_tab_floats(P) * sizeof(float) + (size_t)P.scattering_r_size * DL * 2 * sizeof(float4);
 }
 
 template <bool ORDER2>
 __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
-                                                      Tex3 A0, Tex3 A1, DensityDims dd, float4* __restrict__ tab,
+                                                      Tex3 A0, Tex3 A1, DensityDims dd, float* __restrict__ tab,
                                                       float4* __restrict__ gnd, int r0) {
-    constexpr int E = DensityCfg<ORDER2>::E, TT = DensityCfg<ORDER2>::T;
+    constexpr int ENT = DensityCfg<ORDER2>::ENT, TT = DensityCfg<ORDER2>::T;
     const int l = blockIdx.y, z = r0 + blockIdx.z;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
@@ -135,14 +141,25 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
     F uvwz[4];
     a.ScatteringUvwz(r, ct, mu_s, F(0.f), hits, uvwz);                                // scattering.h:144-145
     const F nn = F((float)dd.nu);
-    const F ux = (F((float)k) + uvwz[1]) / nn;                                        // scattering.h:149
+    const F ux0 = (F((float)k) + uvwz[1]) / nn;                                       // scattering.h:149, tex_x = k
+    const F ux1 = (F((float)k) + F(1.f) + uvwz[1]) / nn;                              // scattering.h:151, tex_x + 1
+    const bool last = k + 1 >= dd.nu;                                                 // no knot beyond: delta 0
     const int tile = ms / dd.ms_tile, msl = ms % dd.ms_tile;
-    const size_t o = ((((size_t)z * dd.tiles + tile) * DL + l) * TT + (size_t)msl * dd.nu + k) * E;
-    V4<F> s0 = sample<F>(A0, ux, uvwz[2], uvwz[3]);
-    tab[o] = make_float4(s0.x.v, s0.y.v, s0.z.v, 0.f);
+    float* o = tab + ((((size_t)z * dd.tiles + tile) * DL + l) * TT + (size_t)msl * dd.nu + k) * ENT;
+    const V4<F> s0 = sample<F>(A0, ux0, uvwz[2], uvwz[3]);
+    const V4<F> s1 = last ? s0 : sample<F>(A0, ux1, uvwz[2], uvwz[3]);
     if (ORDER2) {
-        V4<F> s1 = sample<F>(A1, ux, uvwz[2], uvwz[3]);
-        tab[o + 1] = make_float4(s1.x.v, s1.y.v, s1.z.v, 0.f);
+        const V4<F> m0 = sample<F>(A1, ux0, uvwz[2], uvwz[3]);
+        const V4<F> m1 = last ? m0 : sample<F>(A1, ux1, uvwz[2], uvwz[3]);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        o4[0] = make_float4(s0.x.v, s1.x.v - s0.x.v, s0.y.v, s1.y.v - s0.y.v);
+        o4[1] = make_float4(s0.z.v, s1.z.v - s0.z.v, m0.x.v, m1.x.v - m0.x.v);
+        o4[2] = make_float4(m0.y.v, m1.y.v - m0.y.v, m0.z.v, m1.z.v - m0.z.v);
+    } else {
+        float2* o2 = reinterpret_cast<float2*>(o);
+        o2[0] = make_float2(s0.x.v, s1.x.v - s0.x.v);
+        o2[1] = make_float2(s0.y.v, s1.y.v - s0.y.v);
+        o2[2] = make_float2(s0.z.v, s1.z.v - s0.z.v);
     }
     if (e == 0) {   // per-(r, theta) ground constants, scattering_density.comp:50-60, :81-87
         float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
@@ -168,45 +185,53 @@ template <int OFF> __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
     return v;
 }
-__device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; callers guarantee a normal, positive x
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+template <int OFF> __device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(OFF));
+    return v;
 }
 template <int OFF> __device__ __forceinline__ float lds32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
     return v;
 }
+__device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; callers guarantee a normal, positive x
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <bool ORDER2>
 __global__ void __launch_bounds__(256, 2)
-k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float4* __restrict__ tabG,
+k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float* __restrict__ tabG,
                const float4* __restrict__ gndG, const float4* __restrict__ dE_row0, uint2* __restrict__ out, int r0,
                uint32_t magic_tab, uint32_t magic_row) {
     typedef DensityCfg<ORDER2> C;
-    constexpr int E = C::E, TT = C::T, NWARPS = C::NWARPS;
-    constexpr uint32_t L_STRIDE = TT * E * sizeof(float4);
+    constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
+    constexpr int ENT_B = ENT * 4;                       // bytes per table entry
+    constexpr int L_STRIDE = TT * ENT_B;                 // bytes per theta row block
+    constexpr int TAB_B = DL * L_STRIDE;                 // 96 KiB
+    // shared memory map (bytes): [table TAB_B][geo TT*16][Wt DL*32*16, later reused as outS TT*16][gnd DL*32][Erow nE*24][mbar 8]
+    constexpr int GEO_OFF = TAB_B, WT_OFF = GEO_OFF + TT * 16, GND_OFF = WT_OFF + DL * 32 * 16, EROW_OFF = GND_OFF + DL * 32;
+    static_assert(TT * 16 <= DL * 32 * 16, "outS aliases WtS");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [table: DL*TT*E float4][geo: TT float4][outS: TT float4][Wt: DL*32 float4][gnd: DL*2 float4][Erow: n float4][mbar]
-    float4* tabS = reinterpret_cast<float4*>(smem_raw);
-    float4* geoS = tabS + DL * TT * E;
-    float4* outS = geoS + TT;
-    float4* WtS = outS + TT;
-    float4* gndS = WtS + DL * 32;
-    float4* ErowS = gndS + DL * 2;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(ErowS + P.irradiance_mu_s_size);
+    float4* geoS = reinterpret_cast<float4*>(smem_raw + GEO_OFF);
+    float4* WtS = reinterpret_cast<float4*>(smem_raw + WT_OFF);
+    float4* outS = WtS;
+    float4* gndS = reinterpret_cast<float4*>(smem_raw + GND_OFF);
+    float2* ErowS = reinterpret_cast<float2*>(smem_raw + EROW_OFF);
+    const int nE = P.irradiance_mu_s_size;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + EROW_OFF + nE * 24);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    constexpr uint32_t tab_bytes = DL * L_STRIDE;
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, tab_bytes);
-        tma_bulk_g2s(tabS, tabG + ((size_t)z * dd.tiles + tile) * DL * TT * E, tab_bytes, bar);
+        mbar_expect_tx(bar, TAB_B);
+        tma_bulk_g2s(smem_raw, tabG + ((size_t)z * dd.tiles + tile) * DL * TT * ENT, TAB_B, bar);
     }
 
     A<F> a(P);
@@ -223,7 +248,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             F ox = f_sqrt(F(1.f) - mu * mu);
             F sx = ox == F(0.f) ? F(0.f) : (nu - mu * mu_s) / ox;
             F sy = f_sqrt(f_max(F(1.f) - sx * sx - mu_s * mu_s, F(0.f)));
-            g = make_float4(sx.v, sy.v, mu_s.v, __int_as_float(msl * dd.nu * E));
+            g = make_float4(sx.v, sy.v, mu_s.v, __int_as_float(msl * dd.nu * ENT_B));   // .w: byte offset of the texel's rows
         }
         geoS[t] = g;
     }
@@ -250,7 +275,12 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         }
     }
     for (int e = tid; e < DL * 2; e += NWARPS * 32) gndS[e] = __ldg(gndG + (size_t)z * DL * 2 + e);
-    for (int e = tid; e < P.irradiance_mu_s_size; e += NWARPS * 32) ErowS[e] = __ldg(dE_row0 + e);
+    for (int e = tid; e < nE; e += NWARPS * 32) {   // row 0 of delta_irradiance as (value, delta) pairs
+        const float4 v0 = __ldg(dE_row0 + e), v1 = __ldg(dE_row0 + min(e + 1, nE - 1));
+        ErowS[e * 3] = make_float2(v0.x, v1.x - v0.x);
+        ErowS[e * 3 + 1] = make_float2(v0.y, v1.y - v0.y);
+        ErowS[e * 3 + 2] = make_float2(v0.z, v1.z - v0.z);
+    }
     __syncthreads();
 
     // ---- per-lane constants: the weights of phi sample `lane` for the 16 theta rows (registers) ------------
@@ -267,7 +297,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     const float hn = 0.5f * (float)(dd.nu - 1);
     const float MAGIC = 8388608.f;   // 2^23: x + MAGIC rounded down leaves floor(x) in the low mantissa bits
     // GetIrradiance at r = bottom lands on row 0: u*N - 0.5 = (mu_s*0.5 + 0.5)*(N - 1)
-    const float e_c = 0.5f * (float)(P.irradiance_mu_s_size - 1);
+    const float e_c = 0.5f * (float)(nE - 1);
     float kR = 0.f, kMR = 0.f, g2p1 = 0.f, m2g = 0.f;
     if (ORDER2) {
         const float g = P.mie_phase_function_g;
@@ -277,15 +307,13 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         g2p1 = 1.f + g * g;
         m2g = -2.f * g;
     }
-    // (bits(x + MAGIC) << 4) == 0xB0000000 + 16*floor(x)  (mod 2^32): fold the constant into the base address.
-    // The constants arrive as kernel arguments on purpose: as literals ptxas splits them off the base again and
-    // spends an extra IADD3 per load.
-    constexpr int GND_OFF = (DL * TT * E + 2 * TT + DL * 32) * (int)sizeof(float4);
-    constexpr int EROW_OFF = GND_OFF + DL * 2 * (int)sizeof(float4);
+    // bits(x + MAGIC) * S == 0x4B000000 * S + S * floor(x)  (mod 2^32): the constant is folded into the base address.
+    // It arrives as a kernel argument on purpose: as a literal ptxas splits it off again and pays an IADD3 per load.
     uint32_t sbase = smem_u32(smem_raw);
     asm volatile("" : "+r"(sbase));           // one register for every region; offsets below are immediates
     const uint32_t tab_base = sbase - magic_tab;
     const uint32_t erow_t = sbase - magic_row;
+    __syncthreads();                          // every warp holds its weights: WtS may now be reused as outS
 
     mbar_wait(bar, 0);
 
@@ -302,43 +330,42 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             const float sc = n2 > 0.999998f ? 0.999999f * rsqrt_fast(n2) : 1.f;
             q *= sc; mus *= sc;
         }
-        const uint32_t row_t = tab_base + (uint32_t)__float_as_int(geo.w) * (uint32_t)sizeof(float4);
+        const uint32_t row_t = tab_base + (uint32_t)__float_as_int(geo.w);
         float ar = 0.f, ag = 0.f, ab = 0.f;
 #define FB_DENSITY_STEP(l)                                                                                              \
         {                                                                                                               \
             const float nu1 = fmaf(mus, CT16[l], q * ST16[l]);                                                          \
             const float tcx = fmaf(nu1, hn, hn);                                  /* scattering.h:146, in [0, nu-1) */  \
             const float tm = __fadd_rd(tcx, MAGIC);                                                                     \
-            const float f = tcx - (tm - MAGIC);                                                                         \
-            const uint32_t addr = row_t + (__float_as_uint(tm) << (ORDER2 ? 5 : 4));                                    \
+            const float f = tcx - (tm - MAGIC);                                   /* scattering.h:148 */                \
+            const uint32_t addr = row_t + __float_as_uint(tm) * (uint32_t)ENT_B;                                        \
             float Lr, Lg, Lb;                                                                                           \
             if (ORDER2) {                                                                                               \
-                const float4 r0v = lds128<(l) * L_STRIDE>(addr), m0v = lds128<(l) * L_STRIDE + 16>(addr);               \
-                const float4 r1v = lds128<(l) * L_STRIDE + 32>(addr), m1v = lds128<(l) * L_STRIDE + 48>(addr);          \
+                const float4 t0 = lds128<(l) * L_STRIDE>(addr), t1 = lds128<(l) * L_STRIDE + 16>(addr),                 \
+                             t2 = lds128<(l) * L_STRIDE + 32>(addr);                                                    \
                 const float pr = fmaf(nu1 * kR, nu1, kR);                         /* util.h:26-29 */                    \
-                const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));                                                          \
+                const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));                                                      \
                 const float pm = pr * kMR * (rs * rs * rs);                       /* util.h:31-34: x^-1.5 = rsqrt^3 */  \
-                const float rr = fmaf(f, r1v.x - r0v.x, r0v.x), rg = fmaf(f, r1v.y - r0v.y, r0v.y),                     \
-                            rb = fmaf(f, r1v.z - r0v.z, r0v.z);                                                         \
-                const float mr = fmaf(f, m1v.x - m0v.x, m0v.x), mg = fmaf(f, m1v.y - m0v.y, m0v.y),                     \
-                            mb = fmaf(f, m1v.z - m0v.z, m0v.z);                                                         \
-                Lr = fmaf(mr, pm, rr * pr); Lg = fmaf(mg, pm, rg * pr); Lb = fmaf(mb, pm, rb * pr);                     \
+                Lr = fmaf(fmaf(f, t1.w, t1.z), pm, fmaf(f, t0.y, t0.x) * pr);     /* scattering.h:172-173 */            \
+                Lg = fmaf(fmaf(f, t2.y, t2.x), pm, fmaf(f, t0.w, t0.z) * pr);                                           \
+                Lb = fmaf(fmaf(f, t2.w, t2.z), pm, fmaf(f, t1.y, t1.x) * pr);                                           \
             } else {                                                                                                    \
-                const float4 v0 = lds128<(l) * L_STRIDE>(addr), v1 = lds128<(l) * L_STRIDE + 16>(addr);                 \
-                Lr = fmaf(f, v1.x - v0.x, v0.x); Lg = fmaf(f, v1.y - v0.y, v0.y); Lb = fmaf(f, v1.z - v0.z, v0.z);      \
+                const float2 cr = lds64<(l) * L_STRIDE>(addr), cg = lds64<(l) * L_STRIDE + 8>(addr),                    \
+                             cb = lds64<(l) * L_STRIDE + 16>(addr);                                                     \
+                Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);                           \
             }                                                                                                           \
             if (gmask & (1u << (l))) {                                            /* warp-uniform */                    \
-                const float4 G = lds128<GND_OFF + (l) * 32>(sbase);                          /* (G.rgb, n_x) */                    \
-                const float gz = lds32<GND_OFF + (l) * 32 + 16>(sbase);                                                        \
+                const float4 G = lds128<GND_OFF + (l) * 32>(sbase);               /* (G.rgb, n_x) */                    \
+                const float gz = lds32<GND_OFF + (l) * 32 + 16>(sbase);                                                 \
                 const float musg = fmaf(q, G.w, mus * gz);                        /* dot(ground_normal, omega_s) */     \
                 const float te = fmaf(musg, e_c, e_c);                            /* irradiance.h:20-30, r = bottom */  \
                 const float em = __fadd_rd(te, MAGIC);                                                                  \
                 const float fe = te - (em - MAGIC);                                                                     \
-                const uint32_t ea = erow_t + (__float_as_uint(em) << 4);                                             \
-                const float4 e0 = lds128<EROW_OFF>(ea), e1 = lds128<EROW_OFF + 16>(ea);                                                   \
-                Lr = fmaf(G.x, fmaf(fe, e1.x - e0.x, e0.x), Lr);                                                        \
-                Lg = fmaf(G.y, fmaf(fe, e1.y - e0.y, e0.y), Lg);                                                        \
-                Lb = fmaf(G.z, fmaf(fe, e1.z - e0.z, e0.z), Lb);                                                        \
+                const uint32_t ea = erow_t + __float_as_uint(em) * 24u;                                                 \
+                const float2 er = lds64<EROW_OFF>(ea), eg = lds64<EROW_OFF + 8>(ea), eb = lds64<EROW_OFF + 16>(ea);     \
+                Lr = fmaf(G.x, fmaf(fe, er.y, er.x), Lr);                                                               \
+                Lg = fmaf(G.y, fmaf(fe, eg.y, eg.x), Lg);                                                               \
+                Lb = fmaf(G.z, fmaf(fe, eb.y, eb.x), Lb);                                                               \
             }                                                                                                           \
             ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);                               \
         }
@@ -367,7 +394,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
 
 template <bool ORDER2> static size_t density_smem(const FbParams& P) {
     typedef DensityCfg<ORDER2> C;
-    return ((size_t)DL * C::T * C::E + 2 * C::T + DL * 32 + DL * 2 + P.irradiance_mu_s_size) * sizeof(float4) + 16;
+    return (size_t)DL * C::T * C::ENT * 4 + C::T * 16 + DL * 32 * 16 + DL * 32 + (size_t)P.irradiance_mu_s_size * 24 + 16;
 }
 
 template <bool ORDER2>
@@ -376,8 +403,8 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     const FbParams& P = c.P;
     const DensityDims d = density_dims(P, C::T);
     const size_t smem = density_smem<ORDER2>(P);
-    float4* tab = reinterpret_cast<float4*>(c.img.scratch);
-    float4* gnd = tab + density_tab_float4(P);
+    float* tab = c.img.scratch;
+    float4* gnd = reinterpret_cast<float4*>(tab + density_tab_floats(P));
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     dim3 gp((W + 255) / 256, DL, r1 - r0);
     dim3 gm(d.tiles, P.scattering_mu_size, r1 - r0);
@@ -388,7 +415,7 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     if (e != cudaSuccess) return e;
     k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance,
                                                                   c.img.scattering_density, r0,
-                                                                  ORDER2 ? 0x60000000u : 0xB0000000u, 0xB0000000u);
+                                                                  0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u);
     return cudaGetLastError();
 }
 
