@@ -475,35 +475,34 @@ cudaError_t transmittance(const LaunchCtx& c) {
 cudaError_t direct_irradiance(const LaunchCtx& c) { return ref::direct_irradiance(c); }   // 1 024 threads, one tap each
 
 // ---------------------------------------------------------------------------------------------
-// indirect_irradiance.comp — one WARP per texel (1 024 texels x 1 024 directions: one thread per texel
-// would leave 140 SMs idle).  Lane i takes phi samples i and i+32 of every theta row; each sample is the
-// shader's 4-D look-up, as written, in xf; the hemisphere sum is a __shfl_xor tree.
+// indirect_irradiance.comp — one 4-warp CTA per texel (1 024 texels x 1 024 directions: one thread per texel
+// would leave 140 SMs idle).  A thread takes one phi sample of 8 theta rows; each sample is the shader's 4-D
+// look-up, as written, in xf; the hemisphere sum is a __shfl_xor tree + a 4-way shared-memory add.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_indirect_irradiance(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg,
                                                              Tex3 dR, Tex3 dM, Tex3 dMS, int order, float4* __restrict__ dE,
                                                              float4* __restrict__ E) {
-    const int lane = threadIdx.x & 31;
-    const int texel = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // one CTA (4 warps) per texel: thread t takes phi sample (t & 63) of the theta rows j = (t >> 6), +2, +4, ...
+    __shared__ float part[4][3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int texel = blockIdx.x;
     const int W = P.irradiance_mu_s_size;
-    if (texel >= W * P.irradiance_r_size) return;
     const int x = texel % W, y = texel / W;
     A<F> a(P);
     F r, mu_s;
     a.RMuSFromIrradianceUnit(F((float)x) / F((float)(W - 1)), F((float)y) / F((float)(P.irradiance_r_size - 1)), r, mu_s);
     const F dphi = F(FB_PI_F) / F(32.f), dtheta = F(FB_PI_F) / F(32.f);
     const V omega_s(f_sqrt(F(1.f) - mu_s * mu_s), F(0.f), mu_s);
+    const int i = tid & 63;
+    const F cp = F(tg.cp64[i]), sp = F(tg.sp64[i]);
     float ax = 0.f, ay = 0.f, az = 0.f;
-    for (int j = 0; j < 16; ++j) {
+    for (int j = tid >> 6; j < 16; j += 2) {
         const F ct = F(tg.ct32[j]), st = F(tg.st32[j]);
         const F dw = dtheta * dphi * st;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int i = lane + 32 * half;
-            const V w(F(tg.cp64[i]) * st, F(tg.sp64[i]) * st, ct);
-            const F nu = dot(w, omega_s);
-            const V t = a.ScatteringOrder(dR, dM, dMS, r, w.z, mu_s, nu, false, order) * w.z * dw;
-            ax += t.x.v; ay += t.y.v; az += t.z.v;
-        }
+        const V w(cp * st, sp * st, ct);
+        const F nu = dot(w, omega_s);
+        const V t = a.ScatteringOrder(dR, dM, dMS, r, w.z, mu_s, nu, false, order) * w.z * dw;
+        ax += t.x.v; ay += t.y.v; az += t.z.v;
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
@@ -511,7 +510,12 @@ __global__ void __launch_bounds__(128) k_indirect_irradiance(const __grid_consta
         ay += __shfl_xor_sync(0xffffffffu, ay, s);
         az += __shfl_xor_sync(0xffffffffu, az, s);
     }
-    if (lane == 0) {
+    if (lane == 0) { part[warp][0] = ax; part[warp][1] = ay; part[warp][2] = az; }
+    __syncthreads();
+    if (tid == 0) {
+        ax = (part[0][0] + part[1][0]) + (part[2][0] + part[3][0]);
+        ay = (part[0][1] + part[1][1]) + (part[2][1] + part[3][1]);
+        az = (part[0][2] + part[1][2]) + (part[2][2] + part[3][2]);
         dE[texel] = make_float4(ax, ay, az, 0.f);                                      // indirect_irradiance.comp:72
         const float4 e = E[texel];                                                     // :73
         E[texel] = make_float4(__fadd_rn(ax, e.x), __fadd_rn(ay, e.y), __fadd_rn(az, e.z), __fadd_rn(0.f, e.w));
@@ -520,9 +524,9 @@ __global__ void __launch_bounds__(128) k_indirect_irradiance(const __grid_consta
 
 cudaError_t indirect_irradiance(const LaunchCtx& c, int order) {
     const int texels = c.P.irradiance_mu_s_size * c.P.irradiance_r_size;
-    k_indirect_irradiance<<<(texels + 3) / 4, 128, 0, c.stream>>>(c.P, c.trig, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie),
-                                                                   texS(c, c.img.delta_multiple_scattering), order,
-                                                                   c.img.delta_irradiance, c.img.irradiance);
+    k_indirect_irradiance<<<texels, 128, 0, c.stream>>>(c.P, c.trig, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie),
+                                                        texS(c, c.img.delta_multiple_scattering), order,
+                                                        c.img.delta_irradiance, c.img.irradiance);
     return cudaGetLastError();
 }
 
@@ -613,18 +617,24 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     return cudaGetLastError();
 }
 
-struct MultiNode {       // per trapezoid node, block-uniform
-    float d, inv_r;      // node distance, 1 / r_i
-    float trw[3];        // GetTransmittance(r, mu, d_i) * dx * trapezoid weight
-    float fy, fz;        // (mu, r) interpolation cell of GetScattering(r_i, mu_i, ., ., hits)
-    int y0, y1, z0, z1;
+struct MultiNode {       // per trapezoid node, block-uniform; three 16-byte words so each is one (broadcast) LDS.128
+    float4 w;            // bilinear weights of the (mu, r) cell of GetScattering(r_i, mu_i, ., ., hits): (y0z0, y1z0, y0z1, y1z1)
+    uint4 off;           // texel offsets of those four rows in the density table
+    float4 t;            // GetTransmittance(r, mu, d_i) * dx * trapezoid weight (rgb), node distance d_i
+    float inv_r, pad0, pad1, pad2;   // 1 / r_i
 };
+
+__device__ __forceinline__ float sqrt_fast(float x) {   // MUFU-based, ~1 ulp; used only where the result is well-conditioned
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
                                                               uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MultiNode* nodes = reinterpret_cast<MultiNode*>(smem_raw);
-    float4* slab = reinterpret_cast<float4*>(smem_raw + ((sizeof(MultiNode) * NS + 15) / 16) * 16);
+    float4* slab = reinterpret_cast<float4*>(smem_raw + sizeof(MultiNode) * NS);
     const int NU = P.scattering_nu_size, MS = P.scattering_mu_s_size, W = NU * MS;
     const int x = threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
     A<F> a(P);
@@ -640,13 +650,17 @@ __global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_const
         const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);
         F uvwz[4];
         a.ScatteringUvwz(r_i, mu_i, F(0.f), F(0.f), hits, uvwz);                        // u_mu, u_r of scattering.h:7-60
-        MultiNode n;
+        int y0, y1, z0, z1;
         F fy, fz;
-        tex_axis(uvwz[2], P.scattering_mu_size, n.y0, n.y1, fy);
-        tex_axis(uvwz[3], P.scattering_r_size, n.z0, n.z1, fz);
-        n.fy = fy.v; n.fz = fz.v;
-        n.d = d.v; n.inv_r = (F(1.f) / r_i).v;
-        n.trw[0] = (tr.x * w).v; n.trw[1] = (tr.y * w).v; n.trw[2] = (tr.z * w).v;
+        tex_axis(uvwz[2], P.scattering_mu_size, y0, y1, fy);
+        tex_axis(uvwz[3], P.scattering_r_size, z0, z1, fz);
+        const float gy = 1.f - fy.v, gz = 1.f - fz.v;
+        MultiNode n;
+        n.w = make_float4(gy * gz, fy.v * gz, gy * fz.v, fy.v * fz.v);
+        n.off = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W), (unsigned)((z0 * P.scattering_mu_size + y1) * W),
+                           (unsigned)((z1 * P.scattering_mu_size + y0) * W), (unsigned)((z1 * P.scattering_mu_size + y1) * W));
+        n.t = make_float4((tr.x * w).v, (tr.y * w).v, (tr.z * w).v, d.v);
+        n.inv_r = (F(1.f) / r_i).v; n.pad0 = n.pad1 = n.pad2 = 0.f;
         nodes[i] = n;
     }
     // per-texel constants of the 4-D look-up: the nu slice pair (scattering.h:146-152) ...
@@ -660,41 +674,42 @@ __global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_const
     const float H2 = top * top - bot * bot, b2 = bot * bot, Hh = sqrtf(H2);
     const float dmin = top - bot, inv_span = 1.f / (Hh - dmin);
     const float Ac = -2.f * P.mu_s_min * bot / (Hh - dmin), minvA = -1.f / Ac;
-    const float cu1 = 1.f - 1.f / (float)MS, cu0 = 0.5f / (float)MS;
-    const float tmax = __int_as_float(__float_as_int((float)(MS - 1)) - 1);
+    // u * MS - 0.5 with u = 0.5/MS + xx * (1 - 1/MS)  ==  xx * (MS - 1)
+    const float msm1 = (float)(MS - 1);
+    const float tmax = __int_as_float(__float_as_int(msm1) - 1);
     const float rmus = (r * mu_s).v, nuf = nu.v;
     float ar = 0.f, ag = 0.f, ab = 0.f;
-    const size_t plane = (size_t)P.scattering_mu_size * W;
+    const uint2* dens_x = dens + min(x, W - 1);
     for (int c0 = 0; c0 < NS; c0 += CH) {
         const int cn = min(CH, NS - c0);
         __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
         if (x < W) {
+#pragma unroll 3
             for (int e = 0; e < cn; ++e) {        // stage: (mu, r)-bilinear of the density table at this x, per node
-                const MultiNode& n = nodes[c0 + e];
-                const float4 a00 = unpack_half4(__ldg(dens + n.z0 * plane + (size_t)n.y0 * W + x));
-                const float4 a10 = unpack_half4(__ldg(dens + n.z0 * plane + (size_t)n.y1 * W + x));
-                const float4 a01 = unpack_half4(__ldg(dens + n.z1 * plane + (size_t)n.y0 * W + x));
-                const float4 a11 = unpack_half4(__ldg(dens + n.z1 * plane + (size_t)n.y1 * W + x));
-                const float gy = 1.f - n.fy, gz = 1.f - n.fz;
+                const float4 w = nodes[c0 + e].w;
+                const uint4 o = nodes[c0 + e].off;
+                const float4 a00 = unpack_half4(__ldg(dens_x + o.x)), a10 = unpack_half4(__ldg(dens_x + o.y));
+                const float4 a01 = unpack_half4(__ldg(dens_x + o.z)), a11 = unpack_half4(__ldg(dens_x + o.w));
                 float4 v;
-                v.x = fmaf(fmaf(a11.x, n.fy, a01.x * gy), n.fz, fmaf(a10.x, n.fy, a00.x * gy) * gz);
-                v.y = fmaf(fmaf(a11.y, n.fy, a01.y * gy), n.fz, fmaf(a10.y, n.fy, a00.y * gy) * gz);
-                v.z = fmaf(fmaf(a11.z, n.fy, a01.z * gy), n.fz, fmaf(a10.z, n.fy, a00.z * gy) * gz);
+                v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
+                v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
+                v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
                 v.w = 0.f;
                 slab[e * W + x] = v;
             }
         }
         __syncthreads();
         if (x < W) {
+#pragma unroll 4
             for (int e = 0; e < cn; ++e) {
-                const MultiNode& n = nodes[c0 + e];
-                const float mus_i = fminf(fmaxf(fmaf(n.d, nuf, rmus) * n.inv_r, -1.f), 1.f);   // :38
-                const float disc = fmaf(b2, mus_i * mus_i, H2);                        // params.h:108 at r = bottom
-                const float dd = fmaxf(fmaf(-bot, mus_i, sqrtf(fmaxf(disc, 0.f))), 0.f);
+                const float4 nt = nodes[c0 + e].t;
+                const float inv_r = nodes[c0 + e].inv_r;
+                const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf, rmus) * inv_r, -1.f), 1.f);   // :38
+                // DistanceToTopAtmosphereBoundary(bottom, mu_s_i), params.h:105-110: b^2 (mu^2 - 1) + top^2 > 0 always
+                const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));
                 const float aa = (dd - dmin) * inv_span;
                 const float xx = __fdividef(fmaxf(fmaf(aa, minvA, 1.f), 0.f), 1.f + aa);
-                const float u = fmaf(xx, cu1, cu0);
-                const float t = fminf(fmaxf(fmaf(u, (float)MS, -0.5f), 0.f), tmax);
+                const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);
                 const float tm = __fadd_rd(t, 8388608.f);
                 const int j = __float_as_int(tm) - 0x4B000000;
                 const float fx = t - (tm - 8388608.f);
@@ -702,9 +717,9 @@ __global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_const
                 const float4 p00 = s[kx0], p01 = s[kx0 + 1], p10 = s[kx1], p11 = s[kx1 + 1];
                 const float v0r = fmaf(fx, p01.x - p00.x, p00.x), v0g = fmaf(fx, p01.y - p00.y, p00.y), v0b = fmaf(fx, p01.z - p00.z, p00.z);
                 const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z);
-                ar = fmaf(fmaf(ln, v1r - v0r, v0r), n.trw[0], ar);
-                ag = fmaf(fmaf(ln, v1g - v0g, v0g), n.trw[1], ag);
-                ab = fmaf(fmaf(ln, v1b - v0b, v0b), n.trw[2], ab);
+                ar = fmaf(fmaf(ln, v1r - v0r, v0r), nt.x, ar);
+                ag = fmaf(fmaf(ln, v1g - v0g, v0g), nt.y, ag);
+                ab = fmaf(fmaf(ln, v1b - v0b, v0b), nt.z, ab);
             }
         }
     }
@@ -722,7 +737,7 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     const int nt = ((W + 31) / 32) * 32;
     int CH = 3072 / W;
     CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
-    const size_t smem = ((sizeof(MultiNode) * NS + 15) / 16) * 16 + (size_t)CH * W * sizeof(float4);
+    const size_t smem = sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4);
     cudaError_t e = cudaFuncSetAttribute(k_multiple_scattering, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 g(1, c.P.scattering_mu_size, r1 - r0);
