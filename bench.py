@@ -286,7 +286,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sample = cpu_precompute_ms(16)
+        v, sample = cpu_precompute_ms(2)
         cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -300,6 +300,64 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "render": render}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_hires(args, rank: int, local_rank: int, world: int):
+    """--workload hires: BASELINE.json configs[2] — scattering 128x512x128x32 (2 GiB per 3-D table), transmittance
+    1024x256, 8 orders, ONE atmosphere split into r-slabs across the ranks with NCCL all-gathers of the slabs
+    (fuzzyblue_b200/sharded.py).  Strong scaling: the job is fixed, `value` is the time of one whole precompute."""
+    import torch
+    import torch.distributed as dist
+
+    import fuzzyblue_b200 as fb
+    from fuzzyblue_b200 import sharded
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scale = args.hires_scale          # 1 = the full config; 2 halves every scattering axis (1/16 of the work)
+    p = fb.Parameters(order=8, transmittance_mu_size=1024, transmittance_r_size=256, scattering_r_size=128 // scale,
+                      scattering_mu_size=512 // scale, scattering_mu_s_size=128 // scale, scattering_nu_size=32 // scale)
+    builder = fb.Builder(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    pend = fb.Atmosphere.allocate(builder, p)
+    sp = sharded.ShardedPrecompute(sharded.PendingBackend(pend, stream), p.scattering_r_size, p.order, rank, world)
+    sampler = ClockSampler(local_rank)
+    times = []
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup + args.steps):
+            if i == args.warmup and rank == 0:
+                sampler.start()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sp.run()
+            e1.record(stream)
+            stream.synchronize()
+            if i >= args.warmup:
+                times.append(e0.elapsed_time(e1))
+    total = torch.tensor([sum(times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        ms = float(total.item()) / args.steps
+        W, M, R = p.scattering_nu_size * p.scattering_mu_s_size, p.scattering_mu_size, p.scattering_r_size
+        gather_bytes = sp.gathers // (args.warmup + args.steps) * (W * M * R * 8) * (world - 1) // max(world, 1)
+        line = {"metric": "LUT precompute ms (8 orders, high-resolution dims)", "value": ms, "unit": "ms", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"default Earth physics, T 1024x256, S r{R} x mu{M} x mu_s{p.scattering_mu_s_size} x nu{p.scattering_nu_size}, "
+                                       f"8 orders, r-slab sharded (BASELINE.json configs[2], scale 1/{scale})",
+                           "inputs": "40 bytes of table per texel, far larger than L2", "kernels": "FAST"},
+                "collective": {"all_gathers_per_step": sp.gathers // (args.warmup + args.steps),
+                               "bytes_received_per_rank_per_step": gather_bytes},
+                "clocks": clocks, "gpu_launches": pend.launch_count()}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -389,12 +447,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--render-views", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="default", choices=["default", "hires"])
+    ap.add_argument("--hires-scale", type=int, default=1)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload == "hires":
+        run_hires(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(1024) k_single_scattering(const __grid_constan
     __shared__ SingleNode nodes[NS];
     __shared__ float s_dx;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    const int x = threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
     A<F> a(P);
     F r, mu, mu_s, nu;
     bool hits;
@@ -610,9 +610,8 @@ __global__ void __launch_bounds__(1024) k_single_scattering(const __grid_constan
 
 cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
-    if (W > 1024) return ref::single_scattering(c, r0, r1);
-    const int nt = ((W + 31) / 32) * 32;
-    dim3 g(1, c.P.scattering_mu_size, r1 - r0);
+    const int nt = W >= 256 ? 256 : ((W + 31) / 32) * 32;
+    dim3 g((W + nt - 1) / nt, c.P.scattering_mu_size, r1 - r0);
     k_single_scattering<<<g, nt, 0, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0);
     return cudaGetLastError();
 }
@@ -630,17 +629,33 @@ __device__ __forceinline__ float sqrt_fast(float x) {   // MUFU-based, ~1 ulp; u
     return y;
 }
 
-__global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
+template <int TPT, int NTMAX>   // TPT texels per thread: the CTA covers the whole (nu, mu_s) row, W <= TPT * blockDim.x
+__global__ void __launch_bounds__(NTMAX) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
                                                               uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MultiNode* nodes = reinterpret_cast<MultiNode*>(smem_raw);
     float4* slab = reinterpret_cast<float4*>(smem_raw + sizeof(MultiNode) * NS);
     const int NU = P.scattering_nu_size, MS = P.scattering_mu_s_size, W = NU * MS;
-    const int x = threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
+    const int y = blockIdx.y, z = r0 + blockIdx.z;
     A<F> a(P);
-    F r, mu, mu_s, nu;
+    // per-texel constants of the 4-D look-up: the nu slice pair (scattering.h:146-152) and the sun-angle terms
+    float ln[TPT], rmus[TPT], nuf[TPT], ar[TPT], ag[TPT], ab[TPT];
+    int kx0[TPT], kx1[TPT];
+    F r, mu;
     bool hits;
-    a.TexelToRMuMuSNu((unsigned)min(x, W - 1), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        const int x = min((int)(threadIdx.x + k * blockDim.x), W - 1);
+        F mu_s, nu;
+        a.TexelToRMuMuSNu((unsigned)x, (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);
+        const F tcx = (nu + F(1.f)) / F(2.f) * F((float)(NU - 1));
+        const F txf = f_floor(tcx);
+        ln[k] = (tcx - txf).v;
+        const int tx = min(max((int)txf.v, 0), NU - 1);
+        kx0[k] = tx * MS; kx1[k] = min(tx + 1, NU - 1) * MS;
+        rmus[k] = (r * mu_s).v; nuf[k] = nu.v;
+        ar[k] = ag[k] = ab[k] = 0.f;
+    }
     for (int i = threadIdx.x; i < NS; i += blockDim.x) {
         const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);                        // multiple_scattering.comp:23-26
         const F d = F((float)i) * dx;
@@ -663,13 +678,7 @@ __global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_const
         n.inv_r = (F(1.f) / r_i).v; n.pad0 = n.pad1 = n.pad2 = 0.f;
         nodes[i] = n;
     }
-    // per-texel constants of the 4-D look-up: the nu slice pair (scattering.h:146-152) ...
-    const F tcx = (nu + F(1.f)) / F(2.f) * F((float)(NU - 1));
-    const F txf = f_floor(tcx);
-    const float ln = (tcx - txf).v;
-    const int tx = min(max((int)txf.v, 0), NU - 1);
-    const int kx0 = tx * MS, kx1 = min(tx + 1, NU - 1) * MS;
-    // ... and the mu_s mapping constants (scattering.h:48-56)
+    // the mu_s mapping constants (scattering.h:48-56)
     const float bot = P.bottom_radius, top = P.top_radius;
     const float H2 = top * top - bot * bot, b2 = bot * bot, Hh = sqrtf(H2);
     const float dmin = top - bot, inv_span = 1.f / (Hh - dmin);
@@ -677,73 +686,94 @@ __global__ void __launch_bounds__(1024) k_multiple_scattering(const __grid_const
     // u * MS - 0.5 with u = 0.5/MS + xx * (1 - 1/MS)  ==  xx * (MS - 1)
     const float msm1 = (float)(MS - 1);
     const float tmax = __int_as_float(__float_as_int(msm1) - 1);
-    const float rmus = (r * mu_s).v, nuf = nu.v;
-    float ar = 0.f, ag = 0.f, ab = 0.f;
-    const uint2* dens_x = dens + min(x, W - 1);
     for (int c0 = 0; c0 < NS; c0 += CH) {
         const int cn = min(CH, NS - c0);
         __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
-        if (x < W) {
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            const int x = threadIdx.x + k * blockDim.x;
+            if (x < W) {
+                const uint2* dens_x = dens + x;
 #pragma unroll 3
-            for (int e = 0; e < cn; ++e) {        // stage: (mu, r)-bilinear of the density table at this x, per node
-                const float4 w = nodes[c0 + e].w;
-                const uint4 o = nodes[c0 + e].off;
-                const float4 a00 = unpack_half4(__ldg(dens_x + o.x)), a10 = unpack_half4(__ldg(dens_x + o.y));
-                const float4 a01 = unpack_half4(__ldg(dens_x + o.z)), a11 = unpack_half4(__ldg(dens_x + o.w));
-                float4 v;
-                v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
-                v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
-                v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
-                v.w = 0.f;
-                slab[e * W + x] = v;
+                for (int e = 0; e < cn; ++e) {    // stage: (mu, r)-bilinear of the density table at this x, per node
+                    const float4 w = nodes[c0 + e].w;
+                    const uint4 o = nodes[c0 + e].off;
+                    const float4 a00 = unpack_half4(__ldg(dens_x + o.x)), a10 = unpack_half4(__ldg(dens_x + o.y));
+                    const float4 a01 = unpack_half4(__ldg(dens_x + o.z)), a11 = unpack_half4(__ldg(dens_x + o.w));
+                    float4 v;
+                    v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
+                    v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
+                    v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
+                    v.w = 0.f;
+                    slab[e * W + x] = v;
+                }
             }
         }
         __syncthreads();
-        if (x < W) {
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            if ((int)(threadIdx.x + k * blockDim.x) < W) {
 #pragma unroll 4
-            for (int e = 0; e < cn; ++e) {
-                const float4 nt = nodes[c0 + e].t;
-                const float inv_r = nodes[c0 + e].inv_r;
-                const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf, rmus) * inv_r, -1.f), 1.f);   // :38
-                // DistanceToTopAtmosphereBoundary(bottom, mu_s_i), params.h:105-110: b^2 (mu^2 - 1) + top^2 > 0 always
-                const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));
-                const float aa = (dd - dmin) * inv_span;
-                const float xx = __fdividef(fmaxf(fmaf(aa, minvA, 1.f), 0.f), 1.f + aa);
-                const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);
-                const float tm = __fadd_rd(t, 8388608.f);
-                const int j = __float_as_int(tm) - 0x4B000000;
-                const float fx = t - (tm - 8388608.f);
-                const float4* s = slab + e * W + j;
-                const float4 p00 = s[kx0], p01 = s[kx0 + 1], p10 = s[kx1], p11 = s[kx1 + 1];
-                const float v0r = fmaf(fx, p01.x - p00.x, p00.x), v0g = fmaf(fx, p01.y - p00.y, p00.y), v0b = fmaf(fx, p01.z - p00.z, p00.z);
-                const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z);
-                ar = fmaf(fmaf(ln, v1r - v0r, v0r), nt.x, ar);
-                ag = fmaf(fmaf(ln, v1g - v0g, v0g), nt.y, ag);
-                ab = fmaf(fmaf(ln, v1b - v0b, v0b), nt.z, ab);
+                for (int e = 0; e < cn; ++e) {
+                    const float4 nt = nodes[c0 + e].t;
+                    const float inv_r = nodes[c0 + e].inv_r;
+                    const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf[k], rmus[k]) * inv_r, -1.f), 1.f);   // :38
+                    // DistanceToTopAtmosphereBoundary(bottom, mu_s_i), params.h:105-110: b^2 (mu^2 - 1) + top^2 > 0 always
+                    const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));
+                    const float aa = (dd - dmin) * inv_span;
+                    const float xx = __fdividef(fmaxf(fmaf(aa, minvA, 1.f), 0.f), 1.f + aa);
+                    const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);
+                    const float tm = __fadd_rd(t, 8388608.f);
+                    const int j = __float_as_int(tm) - 0x4B000000;
+                    const float fx = t - (tm - 8388608.f);
+                    const float4* s = slab + e * W + j;
+                    const float4 p00 = s[kx0[k]], p01 = s[kx0[k] + 1], p10 = s[kx1[k]], p11 = s[kx1[k] + 1];
+                    const float v0r = fmaf(fx, p01.x - p00.x, p00.x), v0g = fmaf(fx, p01.y - p00.y, p00.y), v0b = fmaf(fx, p01.z - p00.z, p00.z);
+                    const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z);
+                    ar[k] = fmaf(fmaf(ln[k], v1r - v0r, v0r), nt.x, ar[k]);
+                    ag[k] = fmaf(fmaf(ln[k], v1g - v0g, v0g), nt.y, ag[k]);
+                    ab[k] = fmaf(fmaf(ln[k], v1b - v0b, v0b), nt.z, ab[k]);
+                }
             }
         }
     }
-    if (x >= W) return;
-    const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
-    dMS[o] = pack_half4(ar, ag, ab, 0.f);                                               // multiple_scattering.comp:91
-    const F pr = A<F>::RayleighPhase(nu);                                               // :92
-    const float4 s = unpack_half4(S[o]);
-    S[o] = pack_half4((F(ar) / pr + F(s.x)).v, (F(ag) / pr + F(s.y)).v, (F(ab) / pr + F(s.z)).v, __fadd_rn(0.f, s.w));
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        const int x = threadIdx.x + k * blockDim.x;
+        if (x >= W) continue;
+        const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
+        dMS[o] = pack_half4(ar[k], ag[k], ab[k], 0.f);                                  // multiple_scattering.comp:91
+        const F pr = A<F>::RayleighPhase(F(nuf[k]));                                    // :92
+        const float4 s = unpack_half4(S[o]);
+        S[o] = pack_half4((F(ar[k]) / pr + F(s.x)).v, (F(ag[k]) / pr + F(s.y)).v, (F(ab[k]) / pr + F(s.z)).v, __fadd_rn(0.f, s.w));
+    }
+}
+
+template <int TPT, int NTMAX>
+static cudaError_t multiple_launch(const LaunchCtx& c, int nt, int CH, size_t smem, int r0, int r1) {
+    cudaError_t e = cudaFuncSetAttribute(k_multiple_scattering<TPT, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 g(1, c.P.scattering_mu_size, r1 - r0);
+    k_multiple_scattering<TPT, NTMAX><<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.scattering_density, c.img.delta_multiple_scattering,
+                                                          c.img.scattering, r0, CH);
+    return cudaGetLastError();
 }
 
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
-    if (W > 1024 || c.P.scattering_mu_s_size < 2) return ref::multiple_scattering(c, r0, r1);
-    const int nt = ((W + 31) / 32) * 32;
-    int CH = 3072 / W;
+    if (W > 8192 || c.P.scattering_mu_s_size < 2) return ref::multiple_scattering(c, r0, r1);
+    // default dims: 256 threads, 1 texel each; larger rows: up to 1024 threads x {1, 2, 4, 8} texels
+    const int nt = W <= 1024 ? ((W + 31) / 32) * 32 : 1024;
+    const int tpt = (W + nt - 1) / nt;
+    int CH = 3072 / W;                            // nodes staged per pass: slab = CH * W * 16 B <= 48 KiB (64 KiB for W = 4096)
     CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
     const size_t smem = sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4);
-    cudaError_t e = cudaFuncSetAttribute(k_multiple_scattering, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 g(1, c.P.scattering_mu_size, r1 - r0);
-    k_multiple_scattering<<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.scattering_density, c.img.delta_multiple_scattering,
-                                                     c.img.scattering, r0, CH);
-    return cudaGetLastError();
+    if (smem > 200 * 1024) return ref::multiple_scattering(c, r0, r1);
+    if (nt <= 256) return multiple_launch<1, 256>(c, nt, CH, smem, r0, r1);
+    if (tpt == 1) return multiple_launch<1, 1024>(c, nt, CH, smem, r0, r1);
+    if (tpt == 2) return multiple_launch<2, 1024>(c, nt, CH, smem, r0, r1);
+    if (tpt <= 4) return multiple_launch<4, 1024>(c, nt, CH, smem, r0, r1);
+    return multiple_launch<8, 1024>(c, nt, CH, smem, r0, r1);
 }
 
 int launches_per_stage(int stage) { return stage == FB_STAGE_SCATTERING_DENSITY ? 2 : 1; }

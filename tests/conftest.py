@@ -26,6 +26,16 @@ SMOKE_DIMS = dict(scattering_r_size=8, scattering_mu_size=32, scattering_mu_s_si
 DUMP_DIMS = dict(scattering_r_size=16, scattering_mu_size=64, scattering_mu_s_size=16, scattering_nu_size=4)   # examples/dump.rs:101-107
 
 
+# a thin cut of the high-resolution config (BASELINE.json configs[2]: nu 32, mu_s 128): rows wider than one CTA
+WIDE_DIMS = dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=64, scattering_nu_size=32, order=3)
+
+
+@pytest.fixture(scope="session")
+def oracle_wide_f32():
+    from oracle import oracle as O
+    return O.precompute(O.Params(**WIDE_DIMS), O.F32, keep_history=True)
+
+
 @pytest.fixture(scope="session")
 def oracle_smoke_f32():
     from oracle import oracle as O

@@ -15,7 +15,7 @@ import fuzzyblue_b200 as fb
 from fuzzyblue_b200 import api
 from oracle import oracle as O
 
-from .conftest import DUMP_DIMS, SMOKE_DIMS
+from .conftest import DUMP_DIMS, SMOKE_DIMS, WIDE_DIMS
 
 pytestmark = pytest.mark.gpu
 
@@ -158,6 +158,30 @@ def test_full_precompute(builder, case):
     # single-Mie red channel survives the later orders bit for bit (multiple_scattering.comp:92 adds 0)
     assert np.array_equal(S[..., 3], single_mie_red)
     check("scattering.a == single Mie red", err16(S[..., 3], ref.delta_mie[..., 0]))
+
+
+def test_wide_rows(builder, oracle_wide_f32):
+    """nu = 32, mu_s = 64 (2048-texel rows: several texels per thread in multiple scattering, 8 mu_s tiles in the
+    density kernel, x-tiled single scattering): every stage against the oracle on identical inputs, then end to end."""
+    ref = oracle_wide_f32
+    dims = dict(WIDE_DIMS)
+    order = dims.pop("order")
+    pend = staged(builder, dims, {api.IMAGE_TRANSMITTANCE: ref.transmittance}, order=order)
+    pend.run_stage(api.STAGE_SINGLE_SCATTERING)
+    check("wide delta_rayleigh", err16(pend.download(api.IMAGE_DELTA_RAYLEIGH), ref.delta_rayleigh))
+    check("wide delta_mie", err16(pend.download(api.IMAGE_DELTA_MIE), ref.delta_mie))
+    for o in (2, 3):
+        up = inputs_of_order(ref, o)
+        pend = staged(builder, dims, up, order=order)
+        pend.run_stage(api.STAGE_SCATTERING_DENSITY, order=o)
+        check(f"wide scattering_density(order {o})", err16(pend.download(api.IMAGE_SCATTERING_DENSITY), ref.history[o]["scattering_density"]))
+        pend.upload(api.IMAGE_SCATTERING_DENSITY, ref.history[o]["scattering_density"])
+        pend.run_stage(api.STAGE_INDIRECT_IRRADIANCE, order=o - 1)
+        check(f"wide delta_irradiance(order {o})", err32(pend.download(api.IMAGE_DELTA_IRRADIANCE), ref.history[o]["delta_irradiance"]))
+        pend.run_stage(api.STAGE_MULTIPLE_SCATTERING)
+        check(f"wide delta_multiple_scattering(order {o})",
+              err16(pend.download(api.IMAGE_DELTA_MULTIPLE_SCATTERING), ref.history[o]["delta_multiple_scattering"]))
+        check(f"wide scattering(order {o})", err16(pend.download(api.IMAGE_SCATTERING), ref.history[o]["scattering"]))
 
 
 def test_resubmit_replays_the_same_tables(builder):

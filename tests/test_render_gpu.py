@@ -1,8 +1,10 @@
 """GPU parity of the sky evaluation (shaders/render_sky.frag) and the two shader-library queries, through the C ABI.
 
-Tolerance: 1e-3 relative on the rendered radiance and transmittance per pixel, with an absolute floor of 1e-3 of the
-frame's peak radiance for the colour output: geometry pixels compute `scattering - T * scattering_p`
-(render_sky.h:178), a difference of two nearly equal table look-ups whose relative error is unbounded by construction.
+Tolerance: 1e-3 relative on the rendered radiance and transmittance per pixel, with an absolute floor for the colour
+output of 1e-3 x max(frame peak radiance, 1e-3): geometry pixels compute `scattering - T * scattering_p`
+(render_sky.h:178), a difference of two nearly equal table look-ups of magnitude 0.01..1 whose relative error is
+unbounded by construction (a camera 200 m above the ground looking down sees radiances of 1e-6 there; fp32 rounding of
+the operands alone is 1e-8).  Daylight sky radiance in these units is 1e-2..3e-1.
 """
 import numpy as np
 import pytest
@@ -51,7 +53,7 @@ def test_draw_matches_oracle_over_the_sweep(scene):
         color, transm = scene["renderer"].draw_host(scene["atm"], scene["draws"][k], scene["depths"][k])
         oc, ot = oracle_draw(scene, k)
         assert np.all(np.isfinite(color)) and np.all(np.isfinite(transm))
-        floor = 1e-3 * max(float(np.abs(oc).max()), 1e-9)
+        floor = 1e-3 * max(float(np.abs(oc).max()), 1e-3)
         okc, okt = close(color, oc, floor), close(transm, ot, 1e-6)
         assert okc.all(), (k, float(np.abs(color - oc).max()), floor)
         assert okt.all(), (k, float(np.abs(transm - ot).max()))
