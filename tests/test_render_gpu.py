@@ -53,6 +53,14 @@ def test_draw_matches_oracle_over_the_sweep(scene):
         color, transm = scene["renderer"].draw_host(scene["atm"], scene["draws"][k], scene["depths"][k])
         oc, ot = oracle_draw(scene, k)
         assert np.all(np.isfinite(color)) and np.all(np.isfinite(transm))
+        # A sky pixel (depth 0 => d = inf) seen along a downward ray that misses the ground (mu < 0) makes the shader
+        # itself evaluate inf - inf in `d*d + 2*r*mu*d + r*r` (transmittance.h:43): the reference's transmittance output
+        # is NaN / undefined there (its colour output is fine).  Those pixels are excluded from the transmittance check.
+        undefined = ~np.isfinite(ot)
+        if undefined.any():
+            assert not (scene["depths"][k] > 0)[undefined.any(axis=-1)].any()
+            ot = np.where(undefined, transm, ot)
+        assert np.all(np.isfinite(oc))
         floor = 1e-3 * max(float(np.abs(oc).max()), 1e-3)
         okc, okt = close(color, oc, floor), close(transm, ot, 1e-6)
         assert okc.all(), (k, float(np.abs(color - oc).max()), floor)
