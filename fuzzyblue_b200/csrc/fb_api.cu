@@ -161,6 +161,8 @@ struct FbPending {
     FbAtmosphere* inner;     // Option<Atmosphere>, precompute.rs:2114
     cudaGraphExec_t graph;   // pre-recorded command stream, instantiated lazily
     int launches;
+    cudaStream_t side;       // indirect_irradiance overlaps the density main kernel here (FAST family)
+    cudaEvent_t ev_fork, ev_join;
 };
 
 struct FbRenderer {
@@ -264,6 +266,9 @@ static void free_pending_temps(FbPending* p) {
     p->img.delta_rayleigh = p->img.delta_mie = p->img.scattering_density = p->img.delta_multiple_scattering = nullptr;
     p->img.scratch = nullptr;
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+    if (p->side) { cudaStreamDestroy(p->side); p->side = nullptr; }
+    if (p->ev_fork) { cudaEventDestroy(p->ev_fork); p->ev_fork = nullptr; }
+    if (p->ev_join) { cudaEventDestroy(p->ev_join); p->ev_join = nullptr; }
 }
 
 void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
@@ -301,6 +306,7 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     p->inner = a;
     p->graph = nullptr;
     p->launches = 0;
+    p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
     a->device = b->device;
     a->kernels = b->kernels;
     a->P = *params;
@@ -380,9 +386,30 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
     STAGE(FB_STAGE_DIRECT_IRRADIANCE, 0);      // :1760-1779  -> delta_irradiance
     STAGE(FB_STAGE_SINGLE_SCATTERING, 0);      // :1781-1800
     STAGE(FB_STAGE_CLEAR_IRRADIANCE, 0);       // :1802-1831  direct irradiance is not accumulated
+    const bool overlap = p->builder->kernels == FB_KERNELS_FAST && p->order >= 2;
+    if (overlap && !p->side) {
+        FB_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+        FB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        FB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
     for (uint32_t order = 2; order <= p->order; ++order) {   // :1853
-        STAGE(FB_STAGE_SCATTERING_DENSITY, order);           // :1878-1904, push constant `order`
-        STAGE(FB_STAGE_INDIRECT_IRRADIANCE, order - 1);      // :1927-1953, push constant `order - 1`
+        if (!overlap) {
+            STAGE(FB_STAGE_SCATTERING_DENSITY, order);           // :1878-1904, push constant `order`
+            STAGE(FB_STAGE_INDIRECT_IRRADIANCE, order - 1);      // :1927-1953, push constant `order - 1`
+        } else {
+            // K4 reads delta_irradiance (row 0) only in its preparation kernel, K5 overwrites that image and reads
+            // nothing K4 writes: K5 runs on a side stream next to K4's main kernel and joins before K6 (which
+            // overwrites the delta_multiple_scattering K5 reads).
+            cudaError_t e = fast::scattering_density(c, (int)order, 0, R, p->ev_fork);
+            if (e != cudaSuccess) return cuda_fail(e, "scattering_density launch");
+            if (launches) *launches += fast::launches_per_stage(FB_STAGE_SCATTERING_DENSITY);
+            FB_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+            LaunchCtx cs = c;
+            cs.stream = p->side;
+            if ((st = run_stage(p, cs, FB_STAGE_INDIRECT_IRRADIANCE, order - 1, 0, R, launches)) != FB_OK) return st;
+            FB_CUDA(cudaEventRecord(p->ev_join, p->side));
+            FB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+        }
         STAGE(FB_STAGE_MULTIPLE_SCATTERING, 0);              // :1979-1998
     }
 #undef STAGE

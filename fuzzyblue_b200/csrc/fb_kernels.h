@@ -56,7 +56,8 @@ size_t scratch_bytes(const FbParams& P);
 cudaError_t transmittance(const LaunchCtx& c);
 cudaError_t direct_irradiance(const LaunchCtx& c);
 cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1);
-cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1);
+// `after_prep` (optional) is recorded on c.stream once the stage no longer reads delta_irradiance
+cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cudaEvent_t after_prep = nullptr);
 cudaError_t indirect_irradiance(const LaunchCtx& c, int order);
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1);
 int launches_per_stage(int stage);

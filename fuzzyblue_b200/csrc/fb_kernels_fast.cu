@@ -111,6 +111,7 @@ static inline DensityDims density_dims(const FbParams& P, int T) {
     return d;
 }
 // scratch: table [R][tiles][DL][T][ENT] floats (sized for the order-2 layout, the larger one) + ground [R][DL][2] float4
+// + a snapshot of row 0 of delta_irradiance (so that indirect_irradiance may overwrite the image while the main kernel runs)
 static inline size_t density_tab_floats(const FbParams& P) {
     DensityDims d = density_dims(P, DensityCfg<true>::T);
     return (size_t)P.scattering_r_size * d.tiles * DL * DensityCfg<true>::T * DensityCfg<true>::ENT;
@@ -118,16 +119,19 @@ static inline size_t density_tab_floats(const FbParams& P) {
 
 size_t scratch_bytes(const FbParams& P) {
     if (!density_supported(P)) return 0;
-    return density_tab_floats(P) * sizeof(float) + (size_t)P.scattering_r_size * DL * 2 * sizeof(float4);
+    return density_tab_floats(P) * sizeof(float) + ((size_t)P.scattering_r_size * DL * 2 + P.irradiance_mu_s_size) * sizeof(float4);
 }
 
 template <bool ORDER2>
 __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
                                                       Tex3 A0, Tex3 A1, DensityDims dd, float* __restrict__ tab,
-                                                      float4* __restrict__ gnd, int r0) {
+                                                      float4* __restrict__ gnd, const float4* __restrict__ dE_row0,
+                                                      float4* __restrict__ erow_snapshot, int r0) {
     constexpr int ENT = DensityCfg<ORDER2>::ENT, TT = DensityCfg<ORDER2>::T;
     const int l = blockIdx.y, z = r0 + blockIdx.z;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)   // GetIrradiance(bottom, .) only ever reads row 0
+        for (int i = threadIdx.x; i < P.irradiance_mu_s_size; i += blockDim.x) erow_snapshot[i] = dE_row0[i];
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     if (e >= W) return;
     const int k = e % dd.nu, ms = e / dd.nu;
@@ -398,7 +402,7 @@ template <bool ORDER2> static size_t density_smem(const FbParams& P) {
 }
 
 template <bool ORDER2>
-static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, int r1) {
+static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, int r1, cudaEvent_t after_prep) {
     typedef DensityCfg<ORDER2> C;
     const FbParams& P = c.P;
     const DensityDims d = density_dims(P, C::T);
@@ -408,21 +412,28 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     dim3 gp((W + 255) / 256, DL, r1 - r0);
     dim3 gm(d.tiles, P.scattering_mu_size, r1 - r0);
-    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, gnd, r0);
+    float4* erow = gnd + (size_t)P.scattering_r_size * DL * 2;
+    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, gnd, c.img.delta_irradiance, erow, r0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    // from here on nothing reads delta_irradiance: indirect_irradiance may run concurrently with the main kernel
+    if (after_prep && (e = cudaEventRecord(after_prep, c.stream)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, c.img.delta_irradiance,
+    k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, erow,
                                                                   c.img.scattering_density, r0,
                                                                   0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u);
     return cudaGetLastError();
 }
 
-cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1) {
-    if (!density_supported(c.P) || !c.img.scratch) return ref::scattering_density(c, order, r0, r1);
-    if (order == 2) return density_launch<true>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1);
-    return density_launch<false>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1);
+cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cudaEvent_t after_prep) {
+    if (!density_supported(c.P) || !c.img.scratch) {
+        cudaError_t e = ref::scattering_density(c, order, r0, r1);   // reads delta_irradiance throughout: no early event
+        if (e == cudaSuccess && after_prep) e = cudaEventRecord(after_prep, c.stream);
+        return e;
+    }
+    if (order == 2) return density_launch<true>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1, after_prep);
+    return density_launch<false>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1, after_prep);
 }
 
 // ---------------------------------------------------------------------------------------------
