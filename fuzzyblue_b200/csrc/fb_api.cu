@@ -349,6 +349,9 @@ static LaunchCtx make_ctx(FbPending* p, cudaStream_t s) {
 
 static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order, int r0, int r1, int* launches) {
     const bool fastk = p->builder->kernels == FB_KERNELS_FAST;
+    // a launch reports errors through cudaGetLastError(): make sure an error some earlier, unrelated runtime call in
+    // this thread left behind is not attributed to this stage
+    (void)cudaGetLastError();
     cudaError_t e = cudaSuccess;
     int n = 1;
     switch (stage) {
@@ -370,7 +373,7 @@ static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order
         default: return fail(FB_ERR_INVALID_ARGUMENT, "unknown stage");
     }
     if (fastk && stage <= FB_STAGE_MULTIPLE_SCATTERING) n = fast::launches_per_stage(stage);
-    if (e != cudaSuccess) return cuda_fail(e, "stage launch");
+    if (e != cudaSuccess) return cuda_fail(e, (std::string("stage ") + std::to_string(stage) + " launch").c_str());
     if (launches) *launches += n;
     return FB_OK;
 }

@@ -634,6 +634,11 @@ struct MultiNode {       // per trapezoid node, block-uniform; three 16-byte wor
     float inv_r, pad0, pad1, pad2;   // 1 / r_i
 };
 
+__device__ __forceinline__ float rcp_fast(float x) {    // one MUFU.RCP; callers guarantee a normal x
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float sqrt_fast(float x) {   // MUFU-based, ~1 ulp; used only where the result is well-conditioned
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -704,13 +709,13 @@ __global__ void __launch_bounds__(NTMAX) k_multiple_scattering(const __grid_cons
         for (int k = 0; k < TPT; ++k) {
             const int x = threadIdx.x + k * blockDim.x;
             if (x < W) {
-                const uint2* dens_x = dens + x;
+                const uint32_t xi = (uint32_t)x;
 #pragma unroll 3
                 for (int e = 0; e < cn; ++e) {    // stage: (mu, r)-bilinear of the density table at this x, per node
                     const float4 w = nodes[c0 + e].w;
-                    const uint4 o = nodes[c0 + e].off;
-                    const float4 a00 = unpack_half4(__ldg(dens_x + o.x)), a10 = unpack_half4(__ldg(dens_x + o.y));
-                    const float4 a01 = unpack_half4(__ldg(dens_x + o.z)), a11 = unpack_half4(__ldg(dens_x + o.w));
+                    const uint4 o = nodes[c0 + e].off;   // 32-bit texel indices: one IMAD.WIDE per address
+                    const float4 a00 = unpack_half4(__ldg(dens + (o.x + xi))), a10 = unpack_half4(__ldg(dens + (o.y + xi)));
+                    const float4 a01 = unpack_half4(__ldg(dens + (o.z + xi))), a11 = unpack_half4(__ldg(dens + (o.w + xi)));
                     float4 v;
                     v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
                     v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(NTMAX) k_multiple_scattering(const __grid_cons
                     // DistanceToTopAtmosphereBoundary(bottom, mu_s_i), params.h:105-110: b^2 (mu^2 - 1) + top^2 > 0 always
                     const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));
                     const float aa = (dd - dmin) * inv_span;
-                    const float xx = __fdividef(fmaxf(fmaf(aa, minvA, 1.f), 0.f), 1.f + aa);
+                    const float xx = fmaxf(fmaf(aa, minvA, 1.f), 0.f) * rcp_fast(1.f + aa);   // 1 + a is in [1, 2]
                     const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);
                     const float tm = __fadd_rd(t, 8388608.f);
                     const int j = __float_as_int(tm) - 0x4B000000;

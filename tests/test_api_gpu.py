@@ -1,0 +1,88 @@
+"""GPU tests of the C-ABI object model: batches, error codes, lifetimes, host-buffer entry points."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import fuzzyblue_b200 as fb
+from fuzzyblue_b200 import api, synthetic
+
+from .conftest import SMOKE_DIMS
+
+pytestmark = pytest.mark.gpu
+
+
+def sync():
+    import torch
+    torch.cuda.synchronize()
+
+
+def test_batch_equals_individual_builds():
+    """BASELINE.json config 4 in miniature: distinct atmospheres (Earth-to-Mars radii, random Rayleigh/Mie/ozone) built as
+    one batch on forked streams give bit-identical tables to one-at-a-time builds."""
+    b = fb.Builder(0)
+    params = [fb.Parameters(**SMOKE_DIMS)] + synthetic.random_atmospheres(4, base=fb.Parameters(**SMOKE_DIMS), seed=7)
+    batch = fb.build_batch(b, params, None)
+    sync()
+    for p, pend in zip(params, batch):
+        T, S, E = fb.precompute_host(b, p)
+        a = pend.assert_ready()
+        assert np.array_equal(a.read_scattering(), S) and np.array_equal(a.read_irradiance(), E)
+        assert np.array_equal(a.read_transmittance(), T)
+        assert np.all(np.isfinite(S.astype(np.float32))) and S.astype(np.float32).max() > 0
+    # different physics really gives different tables
+    assert not np.array_equal(fb.precompute_host(b, params[1])[1], fb.precompute_host(b, params[2])[1])
+
+
+def test_error_codes_instead_of_panics():
+    b = fb.Builder(0)
+    with pytest.raises(fb.FuzzyblueError) as e:
+        fb.Atmosphere.build(b, None, fb.Parameters(order=0, **SMOKE_DIMS))
+    assert e.value.status == 1
+    with pytest.raises(fb.FuzzyblueError) as e:
+        fb.Atmosphere.build(b, None, fb.Parameters(scattering_nu_size=1))
+    assert e.value.status == 1
+    with pytest.raises(fb.FuzzyblueError):
+        fb.Builder(1000)
+    pend = fb.Atmosphere.allocate(b, fb.Parameters(**SMOKE_DIMS))
+    with pytest.raises(fb.FuzzyblueError):
+        pend.run_stage(api.STAGE_SCATTERING_DENSITY, order=1)          # scattering_density.comp:22 asserts order >= 2
+    with pytest.raises(fb.FuzzyblueError):
+        pend.run_stage(api.STAGE_SINGLE_SCATTERING, r_begin=5, r_end=3)
+    with pytest.raises(fb.FuzzyblueError):
+        api._check(api._lib().fb_pending_upload(pend._h, api.IMAGE_TRANSMITTANCE, ctypes.c_void_p(1), 7, None))
+    assert api._lib().fb_last_error()
+
+
+def test_pending_outlives_and_temporaries_are_freed():
+    import torch
+    b = fb.Builder(0)
+    free0 = torch.cuda.mem_get_info()[0]
+    pend = fb.Atmosphere.build(b, None, fb.Parameters())
+    sync()
+    borrowed = pend.atmosphere().read_irradiance()
+    atm = pend.assert_ready()                        # frees the 5 temporaries (4 x 8 MiB + scratch), keeps the 3 tables
+    kept = free0 - torch.cuda.mem_get_info()[0]
+    assert np.array_equal(atm.read_irradiance(), borrowed)
+    assert kept <= 16 << 20, kept                    # 8 MiB scattering + 256 KiB + 16 KiB, allocator granularity
+    atm.close()
+    assert free0 - torch.cuda.mem_get_info()[0] <= 2 << 20
+
+
+def test_non_multiple_of_workgroup_dims_are_fully_written():
+    """The reference's truncating dispatch (precompute.rs:1740-1745) leaves edge texels unwritten when a size is not a
+    multiple of the workgroup; here every texel is computed."""
+    dims = dict(transmittance_mu_size=37, transmittance_r_size=11, irradiance_mu_s_size=13, irradiance_r_size=5,
+                scattering_r_size=3, scattering_mu_size=10, scattering_mu_s_size=6, scattering_nu_size=2)
+    for kernels in (api.KERNELS_FAST, api.KERNELS_REFERENCE):
+        T, S, E = fb.precompute_host(fb.Builder(0, kernels=kernels), fb.Parameters(order=3, **dims))
+        assert np.all(T[..., :3] > 0) and np.all(T[..., 3] == 1)
+        assert np.all(np.isfinite(S.astype(np.float32))) and (S.astype(np.float32)[..., :3] > 0).mean() > 0.5
+        assert np.all(np.isfinite(E)) and E.max() > 0
+    from oracle import oracle as O
+    ref = O.precompute(O.Params(order=3, **dims), O.F32)
+    Tf, Sf, Ef = fb.precompute_host(fb.Builder(0), fb.Parameters(order=3, **dims))
+    assert np.max(np.abs(Tf - ref.transmittance) / ref.transmittance) <= 1e-3
+    assert np.max(np.abs(Ef - ref.irradiance) / np.maximum(ref.irradiance, 1e-30)) <= 1e-3
+    e = np.abs(Sf.astype(np.float64) - ref.scattering) / np.maximum(np.abs(ref.scattering), 2.0 ** -14)
+    assert (e > 1e-3).mean() <= 2e-3 and e.max() <= 2e-2
