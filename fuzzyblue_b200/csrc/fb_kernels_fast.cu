@@ -646,7 +646,7 @@ __device__ __forceinline__ float sqrt_fast(float x) {   // MUFU-based, ~1 ulp; u
 }
 
 template <int TPT, int NTMAX>   // TPT texels per thread: the CTA covers the whole (nu, mu_s) row, W <= TPT * blockDim.x
-__global__ void __launch_bounds__(NTMAX) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
+__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
                                                               uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MultiNode* nodes = reinterpret_cast<MultiNode*>(smem_raw);
