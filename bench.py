@@ -135,7 +135,8 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    stride = 8 * max(1, math.ceil(total / 12))
+    # a full default-dims pass costs ~15 s on 16 cores: pick the texel stride that keeps the whole run near two minutes
+    stride = max(1, math.ceil(total * 15.0 / 120.0))
     vals, sample = [], ""
     for i in range(total):
         ms, sample = cpu_precompute_ms(stride)
