@@ -41,42 +41,7 @@ __device__ __forceinline__ bool operator<=(xf a, xf b) { return a.v <= b.v; }
 __device__ __forceinline__ bool operator>=(xf a, xf b) { return a.v >= b.v; }
 __device__ __forceinline__ bool operator==(xf a, xf b) { return a.v == b.v; }
 
-// ---------------------------------------------------------------------------------------------
-// ff: fp32 with contraction allowed, division = MUFU.RCP * x, sqrt = MUFU-based approximations (~1-2 ulp).
-// Only for evaluation paths that are well-conditioned end to end (the per-pixel sky look-ups).
-// ---------------------------------------------------------------------------------------------
-struct ff {
-    float v;
-    __device__ __forceinline__ ff() {}
-    __device__ __forceinline__ constexpr ff(float x) : v(x) {}
-};
-__device__ __forceinline__ ff operator+(ff a, ff b) { return ff(a.v + b.v); }
-__device__ __forceinline__ ff operator-(ff a, ff b) { return ff(a.v - b.v); }
-__device__ __forceinline__ ff operator*(ff a, ff b) { return ff(a.v * b.v); }
-__device__ __forceinline__ ff operator/(ff a, ff b) { return ff(__fdividef(a.v, b.v)); }
-__device__ __forceinline__ ff operator-(ff a) { return ff(-a.v); }
-__device__ __forceinline__ ff& operator+=(ff& a, ff b) { a = a + b; return a; }
-__device__ __forceinline__ bool operator<(ff a, ff b) { return a.v < b.v; }
-__device__ __forceinline__ bool operator>(ff a, ff b) { return a.v > b.v; }
-__device__ __forceinline__ bool operator<=(ff a, ff b) { return a.v <= b.v; }
-__device__ __forceinline__ bool operator>=(ff a, ff b) { return a.v >= b.v; }
-__device__ __forceinline__ bool operator==(ff a, ff b) { return a.v == b.v; }
-
 __device__ __forceinline__ float raw(float a) { return a; }
-__device__ __forceinline__ float raw(ff a) { return a.v; }
-__device__ __forceinline__ ff f_sqrt(ff a) {
-    float y;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(a.v));   // NaN for negative input, like the exact version
-    return ff(y);
-}
-__device__ __forceinline__ ff f_floor(ff a) { return ff(floorf(a.v)); }
-__device__ __forceinline__ ff f_exp(ff a) { return ff(__expf(a.v)); }
-__device__ __forceinline__ ff f_sin(ff a) { return ff(__sinf(a.v)); }
-__device__ __forceinline__ ff f_cos(ff a) { return ff(__cosf(a.v)); }
-__device__ __forceinline__ ff f_pow15(ff a) { return a * f_sqrt(a); }
-__device__ __forceinline__ ff f_min(ff a, ff b) { return ff(fminf(a.v, b.v)); }
-__device__ __forceinline__ ff f_max(ff a, ff b) { return ff(fmaxf(a.v, b.v)); }
-__device__ __forceinline__ bool f_isinf(ff a) { return isinf(a.v); }
 __device__ __forceinline__ float raw(xf a) { return a.v; }
 
 __device__ __forceinline__ float f_sqrt(float a) { return sqrtf(a); }
