@@ -121,6 +121,25 @@ def cpu_precompute_ms(stride: int):
     return total * 1e3, sample
 
 
+def ncu_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_density_main per launch, from the committed `ncu --set full`
+    capture (profiles/r1_precompute_full_raw.csv); None if the capture is not there."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_precompute_full_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        name, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if "k_density_main" in r[name]:
+                return {"bytes_per_launch": float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]],
+                        "source": "profiles/r1_precompute_full_raw.csv (order >= 3 launch; tables are L2-resident)"}
+    except (OSError, ValueError, KeyError, IndexError):
+        pass
+    return None
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -272,7 +291,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
     roofline = {"kernel": "scattering_density", "bound": "fp32", "achieved": achieved, "peak": fma_tflops, "unit": "TFLOP/s",
-                "frac": achieved / fma_tflops if fma_tflops else None, "traffic": None,
+                "frac": achieved / fma_tflops if fma_tflops else None, "traffic": ncu_dram_traffic(),
                 "tally": "hoisted-minimal fp32 flops/sample (92 order 2, 63 order>=3; SURVEY.md §8d), 5.37e8 samples/launch",
                 "achieved_as_written_tflops": written / (dens_ms * 1e-3) / 1e12,
                 "peak_source": "fb_builder_measure_peaks: FFMA issue microbenchmark on this device (measured); "
