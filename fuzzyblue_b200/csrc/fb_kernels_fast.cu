@@ -551,14 +551,31 @@ cudaError_t indirect_irradiance(const LaunchCtx& c, int order) {
 // ---------------------------------------------------------------------------------------------
 constexpr int NS = 51;   // SAMPLE_COUNT + 1, single_scattering.comp:42 / multiple_scattering.comp:21
 
-struct SingleNode {      // per trapezoid node, block-uniform
-    float d, r_d, rd2, d_min, span, e0, e1, cos_h, v;   // v: transmittance-table row coordinate of r_d
-    float tr[3];                                           // GetTransmittance(r, mu, d_i)
-    float rho_r, rho_m;                                    // density * trapezoid weight
+__device__ __forceinline__ float rcp_fast(float x) {    // one MUFU.RCP; callers guarantee a normal x
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {   // MUFU-based, ~1 ulp; used only where the result is well-conditioned
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct SingleNode {      // per trapezoid node, block-uniform; four 16-byte words, each one broadcast LDS.128
+    float4 g0;           // d, 1/r_d, r_d, r_d^2
+    float4 g1;           // d_min, 1/(d_max - d_min), cos_h + e0 (smoothstep origin), 1/(e1 - e0)
+    float4 t;            // GetTransmittance(r, mu, d_i).rgb, fy (row fraction of r_d in the transmittance table)
+    float rho_r, rho_m;  // density * trapezoid weight
+    int row0, row1;      // texel offsets of the two transmittance rows bracketing r_d
 };
 
-__global__ void __launch_bounds__(1024) k_single_scattering(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
-                                                            uint2* __restrict__ dM, uint2* __restrict__ S, int r0) {
+// The per-node quantities (ray geometry, both transmittance taps of GetTransmittance(r, mu, d_i), density profiles,
+// horizon terms, the table rows bracketing r_d) are exact (xf, as written).  The per-texel-per-node remainder — the
+// sun-angle cosine at the node, its u coordinate in the transmittance table, the bilinear blend, the smoothstep —
+// is a smooth, positive, well-conditioned chain and runs in contracted fp32 with MUFU reciprocal / square root.
+__global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
+                                                           uint2* __restrict__ dM, uint2* __restrict__ S, int r0) {
     __shared__ SingleNode nodes[NS];
     __shared__ float s_dx;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
@@ -574,18 +591,21 @@ __global__ void __launch_bounds__(1024) k_single_scattering(const __grid_constan
         const F r_d = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));      // single_scattering.comp:16
         const V tr = a.Transmittance(T, r, mu, d, hits);                                // :19-21
         SingleNode n;
-        n.d = d.v; n.r_d = r_d.v; n.rd2 = (r_d * r_d).v;
+        n.g0 = make_float4(d.v, (F(1.f) / r_d).v, r_d.v, (r_d * r_d).v);
         // GetTransmittanceToSun(r_d, .) and GetTransmittanceTextureUvFromRMu(r_d, .): the r_d-only parts
         const F rho = A<F>::SafeSqrt(r_d * r_d - a.bottom() * a.bottom());              // transmittance.h:14
         const F d_min = a.top() - r_d, d_max = rho + H;
-        n.d_min = d_min.v; n.span = (d_max - d_min).v;
-        n.v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size).v;                   // transmittance.h:21-23
+        const F v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size);               // transmittance.h:21-23
+        int y0, y1;
+        F fy;
+        tex_axis(v, P.transmittance_r_size, y0, y1, fy);
+        n.row0 = y0 * P.transmittance_mu_size; n.row1 = y1 * P.transmittance_mu_size;
         const F sin_h = a.bottom() / r_d;                                               // transmittance.h:67-73
-        n.cos_h = (-f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)))).v;
+        const F cos_h = -f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)));
         const F al = F(P.sun_angular_radius);
         const F e0 = -sin_h * al, e1 = sin_h * al;
-        n.e0 = e0.v; n.e1 = e1.v;
-        n.tr[0] = tr.x.v; n.tr[1] = tr.y.v; n.tr[2] = tr.z.v;
+        n.g1 = make_float4(d_min.v, (F(1.f) / (d_max - d_min)).v, (cos_h + e0).v, (F(1.f) / (e1 - e0)).v);
+        n.t = make_float4(tr.x.v, tr.y.v, tr.z.v, fy.v);
         const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);                         // a power of two: folding it is exact
         n.rho_r = (A<F>::ProfileDensity(P.rayleigh_density, r_d - a.bottom()) * w).v;   // :24-27
         n.rho_m = (A<F>::ProfileDensity(P.mie_density, r_d - a.bottom()) * w).v;
@@ -594,25 +614,36 @@ __global__ void __launch_bounds__(1024) k_single_scattering(const __grid_constan
     }
     __syncthreads();
     if (x >= W) return;
-    const F r_mu_s = r * mu_s;
-    const F tt = a.top() * a.top();
-    V rs(F(0.f)), ms(F(0.f));
+    const float r_mu_s = (r * mu_s).v, nuf = nu.v, tt = P.top_radius * P.top_radius;
+    const float un = (float)(P.transmittance_mu_size - 1);                              // u*N - 0.5 == x_mu * (N - 1)
+    const float umax = __int_as_float(__float_as_int(un) - 1);
+    float rsr = 0.f, rsg = 0.f, rsb = 0.f, msr = 0.f, msg = 0.f, msb = 0.f;
+#pragma unroll 3
     for (int i = 0; i < NS; ++i) {
-        const SingleNode& n = nodes[i];
-        const F r_d = F(n.r_d);
-        const F mu_s_d = A<F>::ClampCosine((r_mu_s + F(n.d) * nu) / r_d);               // :17
+        const float4 g0 = nodes[i].g0, g1 = nodes[i].g1, nt = nodes[i].t;
+        const float mu_s_d = fminf(fmaxf(fmaf(g0.x, nuf, r_mu_s) * g0.y, -1.f), 1.f);   // :17
         // DistanceToTopAtmosphereBoundary(r_d, mu_s_d), params.h:105-110
-        const F disc = F(n.rd2) * (mu_s_d * mu_s_d - F(1.f)) + tt;
-        const F dtop = A<F>::ClampDistance(-r_d * mu_s_d + A<F>::SafeSqrt(disc));
-        const F u = A<F>::CoordFromUnit((dtop - F(n.d_min)) / F(n.span), P.transmittance_mu_size);
-        const V tsun = sample<F>(T, u, F(n.v)).rgb() * f_smoothstep<F>(F(n.e0), F(n.e1), mu_s_d - F(n.cos_h));
-        const V t = V(F(n.tr[0]), F(n.tr[1]), F(n.tr[2])) * tsun;
-        rs = rs + t * F(n.rho_r);
-        ms = ms + t * F(n.rho_m);
+        const float disc = fmaf(g0.w, fmaf(mu_s_d, mu_s_d, -1.f), tt);
+        const float dtop = fmaxf(fmaf(-g0.z, mu_s_d, sqrt_fast(fmaxf(disc, 0.f))), 0.f);
+        const float tu = fminf(fmaxf((dtop - g1.x) * g1.y * un, 0.f), umax);            // transmittance.h:20-22
+        const float tm = __fadd_rd(tu, 8388608.f);
+        const int j = __float_as_int(tm) - 0x4B000000;
+        const float fx = tu - (tm - 8388608.f);
+        const float4 a00 = __ldg(T.p + nodes[i].row0 + j), a10 = __ldg(T.p + nodes[i].row0 + j + 1);
+        const float4 a01 = __ldg(T.p + nodes[i].row1 + j), a11 = __ldg(T.p + nodes[i].row1 + j + 1);
+        float sm = fminf(fmaxf((mu_s_d - g1.z) * g1.w, 0.f), 1.f);                      // smoothstep, transmittance.h:71-73
+        sm = sm * sm * fmaf(-2.f, sm, 3.f);
+        const float b0r = fmaf(fx, a10.x - a00.x, a00.x), b0g = fmaf(fx, a10.y - a00.y, a00.y), b0b = fmaf(fx, a10.z - a00.z, a00.z);
+        const float b1r = fmaf(fx, a11.x - a01.x, a01.x), b1g = fmaf(fx, a11.y - a01.y, a01.y), b1b = fmaf(fx, a11.z - a01.z, a01.z);
+        const float tr_ = fmaf(nt.w, b1r - b0r, b0r) * sm * nt.x, tg_ = fmaf(nt.w, b1g - b0g, b0g) * sm * nt.y,
+                    tb_ = fmaf(nt.w, b1b - b0b, b0b) * sm * nt.z;
+        const float rr = nodes[i].rho_r, rm = nodes[i].rho_m;
+        rsr = fmaf(tr_, rr, rsr); rsg = fmaf(tg_, rr, rsg); rsb = fmaf(tb_, rr, rsb);
+        msr = fmaf(tr_, rm, msr); msg = fmaf(tg_, rm, msg); msb = fmaf(tb_, rm, msb);
     }
     const F dx = F(s_dx);
-    const V ray = rs * dx * V(P.solar_irradiance) * V(P.rayleigh_scattering);           // :62-64
-    const V mie = ms * dx * V(P.solar_irradiance) * V(P.mie_scattering);
+    const V ray = V(F(rsr), F(rsg), F(rsb)) * dx * V(P.solar_irradiance) * V(P.rayleigh_scattering);   // :62-64
+    const V mie = V(F(msr), F(msg), F(msb)) * dx * V(P.solar_irradiance) * V(P.mie_scattering);
     const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
     dR[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, 0.f);
     dM[o] = pack_half4(mie.x.v, mie.y.v, mie.z.v, 0.f);
@@ -634,16 +665,6 @@ struct MultiNode {       // per trapezoid node, block-uniform; three 16-byte wor
     float inv_r, pad0, pad1, pad2;   // 1 / r_i
 };
 
-__device__ __forceinline__ float rcp_fast(float x) {    // one MUFU.RCP; callers guarantee a normal x
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sqrt_fast(float x) {   // MUFU-based, ~1 ulp; used only where the result is well-conditioned
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 template <int TPT, int NTMAX>   // TPT texels per thread: the CTA covers the whole (nu, mu_s) row, W <= TPT * blockDim.x
 __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
