@@ -197,6 +197,27 @@ def test_wide_rows(builder, oracle_wide_f32):
         check(f"wide scattering(order {o})", err16(pend.download(api.IMAGE_SCATTERING), ref.history[o]["scattering"]))
 
 
+@pytest.mark.parametrize("index", [0, 1, 2])
+def test_randomised_atmospheres(builder, family, index):
+    """BASELINE.json config 4 physics (Earth-to-Mars radii, random Rayleigh / Mie / ozone / albedo / sun size) at the
+    reduced dims of tests/smoke.rs: every table of a 3-order precompute against the oracle run on the same block."""
+    from fuzzyblue_b200 import synthetic
+    base = fb.Parameters(order=3, **SMOKE_DIMS)
+    p = synthetic.random_atmospheres(3, base=base, seed=99)[index]
+    op = O.Params(order=3, **SMOKE_DIMS)
+    for name in ("solar_irradiance", "sun_angular_radius", "bottom_radius", "top_radius", "rayleigh_scattering", "mie_scattering",
+                 "mie_extinction", "mie_phase_function_g", "absorbtion_extinction", "ground_albedo", "mu_s_min"):
+        setattr(op, name, getattr(p, name))
+    for name in ("rayleigh_density", "mie_density", "absorbtion_density"):
+        setattr(op, name, tuple(O.Layer(l.width, l.exp_term, l.exp_scale, l.linear_term, l.constant_term) for l in getattr(p, name).layers))
+    assert bytes(p.raw()) == op.pack()
+    ref = O.precompute(op, O.F32)
+    T, S, E = fb.precompute_host(builder, p)
+    check("transmittance", err32(T, ref.transmittance))
+    check("irradiance", err32(E, ref.irradiance))
+    (check if family == "reference" else check_compounded)("scattering", err16(S, ref.scattering))
+
+
 def test_resubmit_replays_the_same_tables(builder):
     p = fb.Parameters(**SMOKE_DIMS)
     pend = fb.Atmosphere.build(builder, None, p)
