@@ -367,15 +367,16 @@ def run_hires(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         ms = float(total.item()) / args.steps
         W, M, R = p.scattering_nu_size * p.scattering_mu_s_size, p.scattering_mu_size, p.scattering_r_size
-        gather_bytes = sp.gathers // (args.warmup + args.steps) * (W * M * R * 8) * (world - 1) // max(world, 1)
+        gather_bytes = sp.bytes_received // (args.warmup + args.steps)
         line = {"metric": "LUT precompute ms (8 orders, high-resolution dims)", "value": ms, "unit": "ms", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"default Earth physics, T 1024x256, S r{R} x mu{M} x mu_s{p.scattering_mu_s_size} x nu{p.scattering_nu_size}, "
                                        f"8 orders, r-slab sharded (BASELINE.json configs[2], scale 1/{scale})",
                            "inputs": "40 bytes of table per texel, far larger than L2", "kernels": "FAST"},
-                "collective": {"all_gathers_per_step": sp.gathers // (args.warmup + args.steps),
-                               "bytes_received_per_rank_per_step": gather_bytes},
+                "collective": {"all_gathers_per_step": sp.gathers // (args.warmup + args.steps), "sub_slab_chunks": sp.chunks,
+                               "bytes_received_per_rank_per_step": gather_bytes,
+                               "overlap": "sub-slab all-gathers on a communication stream behind the next sub-slab's kernels"},
                 "clocks": clocks, "gpu_launches": pend.launch_count()}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -57,23 +57,62 @@ class PendingBackend:
 
 class ShardedPrecompute:
     """The command stream of Atmosphere::build (src/precompute.rs:1671-2048) with the 3-D stages restricted to this
-    rank's r-slab and the exchanges listed above."""
+    rank's r-slab and the exchanges listed above.
 
-    def __init__(self, backend, r_size: int, order: int, rank: int, world: int, group=None):
+    The two big producers (scattering_density before K6, multiple_scattering before the next order) are launched in
+    `chunks` sub-slabs; as soon as a sub-slab has been enqueued its all-gather goes onto a communication stream, so the
+    NVLink transfer of sub-slab c overlaps the computation of sub-slab c+1 (GPU backends; the CPU test backend has no
+    streams and gathers synchronously)."""
+
+    def __init__(self, backend, r_size: int, order: int, rank: int, world: int, group=None, chunks: int = 4):
         self.b, self.order, self.rank, self.world, self.group = backend, order, rank, world, group
         self.r0, self.r1 = slab_of(rank, world, r_size)
         self.r_size = r_size
+        n = self.r1 - self.r0
+        self.chunks = max(c for c in range(1, max(1, min(chunks, n)) + 1) if n % c == 0)
+        if world > 1:   # splitting only pays when a sub-slab is a real transfer (>= 16 MiB); small tables go in one piece
+            t = backend.tensor(api.IMAGE_SCATTERING_DENSITY)
+            while self.chunks > 1 and (t.numel() * t.element_size() // world // self.chunks < (16 << 20) or n % self.chunks):
+                self.chunks -= 1
         self.gathers = 0
+        self.bytes_received = 0          # per rank, summed over all exchanges
+        self._comm = None
+        if world > 1 and getattr(backend, "stream", None) is not None:
+            import torch
+            self._comm = torch.cuda.Stream()
 
-    def _all_gather(self, image: int):
+    def _all_gather(self, image: int, lo: int = 0, hi: int = 0):
+        """All-gather rows [lo, hi) (relative to each rank's slab; default: the whole slab) of `image`."""
         if self.world == 1:
             return
         import torch.distributed as dist
         full = self.b.tensor(image)
         n = self.r_size // self.world
-        views = [full[i * n:(i + 1) * n] for i in range(self.world)]
-        dist.all_gather(views, views[self.rank], group=self.group)
+        hi = hi or n
+        views = [full[i * n + lo:i * n + hi] for i in range(self.world)]
+        if self._comm is None:
+            dist.all_gather(views, views[self.rank], group=self.group)
+        else:
+            import torch
+            ev = torch.cuda.Event()
+            ev.record(self.b.stream)                 # the sub-slab's producer kernel has been enqueued on the compute stream
+            self._comm.wait_event(ev)
+            with torch.cuda.stream(self._comm):
+                dist.all_gather(views, views[self.rank], group=self.group)
         self.gathers += 1
+        self.bytes_received += (self.world - 1) * views[0].numel() * views[0].element_size()
+
+    def _join(self):
+        """Dependent stages on the compute stream wait for every exchange issued so far."""
+        if self._comm is not None:
+            self.b.stream.wait_stream(self._comm)
+
+    def _produce_and_gather(self, stage: int, order: int, image: int, gather: bool = True):
+        m = (self.r1 - self.r0) // self.chunks
+        for c in range(self.chunks):
+            self.b.run_stage(stage, order, self.r0 + c * m, self.r0 + (c + 1) * m)
+            if gather:
+                self._all_gather(image, c * m, (c + 1) * m)
 
     def run(self, gather_result: bool = True):
         b, r0, r1 = self.b, self.r0, self.r1
@@ -84,13 +123,17 @@ class ShardedPrecompute:
         if self.order >= 2:
             self._all_gather(api.IMAGE_DELTA_RAYLEIGH)      # order-2 density halo + indirect irradiance of order 1
             self._all_gather(api.IMAGE_DELTA_MIE)
+            self._join()
         for order in range(2, self.order + 1):
-            b.run_stage(api.STAGE_SCATTERING_DENSITY, order, r0, r1)
-            b.run_stage(api.STAGE_INDIRECT_IRRADIANCE, order - 1)          # replicated: 2-D, reads all r
-            self._all_gather(api.IMAGE_SCATTERING_DENSITY)                 # the ray march of K6 crosses every r
-            b.run_stage(api.STAGE_MULTIPLE_SCATTERING, 0, r0, r1)
-            if order < self.order:
-                self._all_gather(api.IMAGE_DELTA_MULTIPLE_SCATTERING)      # next density halo + next indirect irradiance
+            # K4 in sub-slabs, each gathered behind the next one's computation: the ray march of K6 crosses every r
+            self._produce_and_gather(api.STAGE_SCATTERING_DENSITY, order, api.IMAGE_SCATTERING_DENSITY)
+            b.run_stage(api.STAGE_INDIRECT_IRRADIANCE, order - 1)          # replicated: 2-D, reads all r (previous order)
+            self._join()
+            # K6 likewise; its output feeds the next order's density halo and indirect irradiance
+            self._produce_and_gather(api.STAGE_MULTIPLE_SCATTERING, 0, api.IMAGE_DELTA_MULTIPLE_SCATTERING,
+                                     gather=order < self.order)
+            self._join()
         if gather_result:
             self._all_gather(api.IMAGE_SCATTERING)
+            self._join()
         return self

@@ -106,7 +106,8 @@ def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order):
         assert np.array_equal(got["T"], ref.transmittance)
         assert np.array_equal(got["E"], ref.irradiance)
         assert np.array_equal(got["S"], ref.scattering)           # every rank holds the full, identical final table
-        # 2 single-scattering gathers + per order: density (+ delta_multiple except after the last) + final scattering
+        # 2 single-scattering gathers + per order: density (+ delta_multiple except after the last) + the final table
+        # (tables this small are exchanged in one piece)
         assert int(got["gathers"]) == 2 + (order - 1) + (order - 2) + 1
     # each rank's own slab of the last delta_multiple_scattering is current; the peer's slab is still the previous
     # order's (the last order's temporaries are not exchanged: nothing reads them)
