@@ -64,7 +64,8 @@ class ShardedPrecompute:
     NVLink transfer of sub-slab c overlaps the computation of sub-slab c+1 (GPU backends; the CPU test backend has no
     streams and gathers synchronously)."""
 
-    def __init__(self, backend, r_size: int, order: int, rank: int, world: int, group=None, chunks: int = 4):
+    def __init__(self, backend, r_size: int, order: int, rank: int, world: int, group=None, chunks: int = 4,
+                 min_chunk_bytes: int = 16 << 20):
         self.b, self.order, self.rank, self.world, self.group = backend, order, rank, world, group
         self.r0, self.r1 = slab_of(rank, world, r_size)
         self.r_size = r_size
@@ -72,7 +73,7 @@ class ShardedPrecompute:
         self.chunks = max(c for c in range(1, max(1, min(chunks, n)) + 1) if n % c == 0)
         if world > 1:   # splitting only pays when a sub-slab is a real transfer (>= 16 MiB); small tables go in one piece
             t = backend.tensor(api.IMAGE_SCATTERING_DENSITY)
-            while self.chunks > 1 and (t.numel() * t.element_size() // world // self.chunks < (16 << 20) or n % self.chunks):
+            while self.chunks > 1 and (t.numel() * t.element_size() // world // self.chunks < min_chunk_bytes or n % self.chunks):
                 self.chunks -= 1
         self.gathers = 0
         self.bytes_received = 0          # per rank, summed over all exchanges

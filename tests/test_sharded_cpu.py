@@ -78,12 +78,12 @@ class OracleBackend:
             raise ValueError(stage)
 
 
-def _worker(rank, world, port, order, out_dir):
+def _worker(rank, world, port, order, out_dir, min_chunk_bytes):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p = O.Params(order=order, **DIMS)
     be = OracleBackend(p)
-    sp = sharded.ShardedPrecompute(be, p.scattering_r_size, order, rank, world).run()
+    sp = sharded.ShardedPrecompute(be, p.scattering_r_size, order, rank, world, min_chunk_bytes=min_chunk_bytes).run()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), S=be._np(api.IMAGE_SCATTERING), E=be._np(api.IMAGE_IRRADIANCE),
              T=be._np(api.IMAGE_TRANSMITTANCE), dMS=be._np(api.IMAGE_DELTA_MULTIPLE_SCATTERING), gathers=sp.gathers)
     dist.destroy_process_group()
@@ -96,10 +96,12 @@ def test_slab_partition():
         sharded.slab_of(0, 3, 32)
 
 
-@pytest.mark.parametrize("order", [3])
-def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order):
-    world, port = 2, 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, order, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("order,min_chunk_bytes", [(3, 16 << 20), (3, 0)])
+def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order, min_chunk_bytes):
+    """min_chunk_bytes = 0 forces the sub-slab pipeline (2 chunks per 2-row slab) that large tables use."""
+    world, port = 2, 29500 + (os.getpid() % 2000) + (1 if min_chunk_bytes else 0)
+    mp.spawn(_worker, args=(world, port, order, str(tmp_path), min_chunk_bytes), nprocs=world, join=True)
+    chunks = 1 if min_chunk_bytes else 2
     ref = O.precompute(O.Params(order=order, **DIMS), O.F32)
     for rank in range(world):
         got = np.load(tmp_path / f"rank{rank}.npz")
@@ -108,7 +110,7 @@ def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order):
         assert np.array_equal(got["S"], ref.scattering)           # every rank holds the full, identical final table
         # 2 single-scattering gathers + per order: density (+ delta_multiple except after the last) + the final table
         # (tables this small are exchanged in one piece)
-        assert int(got["gathers"]) == 2 + (order - 1) + (order - 2) + 1
+        assert int(got["gathers"]) == 2 + chunks * ((order - 1) + (order - 2)) + 1
     # each rank's own slab of the last delta_multiple_scattering is current; the peer's slab is still the previous
     # order's (the last order's temporaries are not exchanged: nothing reads them)
     r0 = np.load(tmp_path / "rank0.npz")["dMS"]
