@@ -377,7 +377,8 @@ def run_hires(args, rank: int, local_rank: int, world: int):
                 "collective": {"all_gathers_per_step": sp.gathers // (args.warmup + args.steps), "sub_slab_chunks": sp.chunks,
                                "bytes_received_per_rank_per_step": gather_bytes,
                                "overlap": "sub-slab all-gathers on a communication stream behind the next sub-slab's kernels"},
-                "clocks": clocks, "gpu_launches": pend.launch_count()}
+                "clocks": clocks, "gpu_launches": pend.launch_count() * args.steps // (args.warmup + args.steps),
+                "launches_per_step": pend.launch_count() // (args.warmup + args.steps)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

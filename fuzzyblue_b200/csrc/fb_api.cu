@@ -461,7 +461,10 @@ int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_beg
     if (r_begin >= r_end || r_end > R) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_run_stage: bad r slab");
     DeviceGuard g(p->builder->device);
     LaunchCtx c = make_ctx(p, (cudaStream_t)stream);
-    return run_stage(p, c, stage, order, (int)r_begin, (int)r_end, nullptr);
+    int n = 0;
+    const int st = run_stage(p, c, stage, order, (int)r_begin, (int)r_end, &n);
+    p->launches += n;   // stage-driven pendings accumulate; build / resubmit overwrite with the per-submit count
+    return st;
 }
 
 int fb_pending_image(FbPending* p, int image, void** dev_ptr, size_t* bytes) {

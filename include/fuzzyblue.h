@@ -161,7 +161,8 @@ FB_API int fb_atmosphere_allocate(FbBuilder* b, const FbParams* p, uint32_t orde
  * re-submitting the pre-recorded command buffer, which is what benches/precompute.rs:138-148
  * times.  The stream is replayed from a CUDA graph instantiated on first use. */
 FB_API int fb_pending_resubmit(FbPending* p, void* stream);
-/* Number of kernel launches / memset nodes one submit performs (for launch accounting). */
+/* Number of kernel launches / memset nodes of the last build / resubmit; for a pending driven stage by stage
+ * (fb_atmosphere_allocate + fb_pending_run_stage) the running total since allocation. */
 FB_API int fb_pending_launch_count(const FbPending* p);
 
 /* One stage on the slab r in [r_begin, r_end) of the scattering r axis (3-D stages) or on the whole
