@@ -94,6 +94,7 @@ ABI = {
     "fb_builder_create": (c_int, [c_int, _P(c_void_p)]),
     "fb_builder_destroy": (None, [c_void_p]),
     "fb_builder_set_kernels": (c_int, [c_void_p, c_int]),
+    "fb_builder_trim": (c_int, [c_void_p]),
     "fb_builder_device": (c_int, [c_void_p]),
     "fb_builder_sm_count": (c_int, [c_void_p]),
     "fb_builder_measure_peaks": (c_int, [c_void_p, _P(ctypes.c_double), _P(ctypes.c_double)]),
@@ -298,6 +299,10 @@ class Builder:
 
     def set_kernels(self, kernels: int):
         _check(_lib().fb_builder_set_kernels(self._h, kernels))
+
+    def trim(self):
+        """Return cached device blocks of finished precomputes to the driver."""
+        _check(_lib().fb_builder_trim(self._h))
 
     def device(self) -> int:
         return _lib().fb_builder_device(self._h)

@@ -8,6 +8,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -137,16 +140,73 @@ int fb_params_scattering_extent(const FbParams* p, FbExtent3D* o) {      // :786
 // ---------------------------------------------------------------------------------------------
 // objects
 // ---------------------------------------------------------------------------------------------
+// Device blocks released by a finished precompute are kept (up to `limit` bytes) and handed to the next one of the
+// same dims: cudaMalloc / cudaFree cost ~0.2 ms each and cudaFree synchronises the whole device, which would serialise
+// a batch of independent atmospheres.  Shared by the builder and everything built from it, so an Atmosphere may
+// outlive its Builder (the reference holds an Arc<Builder> for the same reason, precompute.rs:1037).
+struct BlockCache {
+    int device;
+    size_t limit, cached;
+    std::mutex m;
+    std::multimap<size_t, void*> free_blocks;
+    explicit BlockCache(int dev) : device(dev), limit((size_t)8 << 30), cached(0) {}
+    cudaError_t get(void** p, size_t n) {
+        {
+            std::lock_guard<std::mutex> g(m);
+            auto it = free_blocks.find(n);
+            if (it != free_blocks.end()) {
+                *p = it->second;
+                free_blocks.erase(it);
+                cached -= n;
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(p, n);
+        if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back to the driver and retry once
+            (void)cudaGetLastError();
+            trim();
+            e = cudaMalloc(p, n);
+        }
+        return e;
+    }
+    void put(void* p, size_t n) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> g(m);
+            if (cached + n <= limit) {
+                free_blocks.emplace(n, p);
+                cached += n;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> g(m);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached = 0;
+    }
+    ~BlockCache() {
+        int prev = -1;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device);
+        trim();
+        if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    }
+};
+
 struct FbBuilder {
     int device;
     int sm_count;
     int kernels;
     Trig trig;
+    std::shared_ptr<BlockCache> cache;
 };
 
 struct FbAtmosphere {
     int device;
     int kernels;
+    std::shared_ptr<BlockCache> cache;
     FbParams P;
     float4* transmittance;
     float4* irradiance;
@@ -155,6 +215,7 @@ struct FbAtmosphere {
 
 struct FbPending {
     FbBuilder* builder;
+    std::shared_ptr<BlockCache> cache;
     FbParams P;
     uint32_t order;
     Images img;
@@ -236,6 +297,7 @@ int fb_builder_create(int device, FbBuilder** out) {
     b->device = device;
     b->sm_count = prop.multiProcessorCount;
     b->kernels = FB_KERNELS_FAST;
+    b->cache = std::make_shared<BlockCache>(device);
     make_trig(&b->trig);
     *out = b;
     return FB_OK;
@@ -252,16 +314,23 @@ int fb_builder_measure_peaks(FbBuilder* b, double* fp32_fma_tflops, double* sfu_
     cudaError_t e = measure_peaks(b->sm_count, fp32_fma_tflops, sfu_gops);
     return e == cudaSuccess ? FB_OK : cuda_fail(e, "measure_peaks");
 }
+int fb_builder_trim(FbBuilder* b) {
+    if (!b) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_trim: NULL");
+    DeviceGuard g(b->device);
+    b->cache->trim();
+    return FB_OK;
+}
 int fb_builder_device(const FbBuilder* b) { return b ? b->device : -1; }
 int fb_builder_sm_count(const FbBuilder* b) { return b ? b->sm_count : 0; }
 
 static void free_pending_temps(FbPending* p) {
-    cudaFree(p->img.delta_irradiance);
-    cudaFree(p->img.delta_rayleigh);
-    cudaFree(p->img.delta_mie);
-    cudaFree(p->img.scattering_density);
-    cudaFree(p->img.delta_multiple_scattering);
-    cudaFree(p->img.scratch);
+    const size_t b2e = image_bytes(p->P, FB_IMAGE_IRRADIANCE), b3 = bytes3d(p->P);
+    p->cache->put(p->img.delta_irradiance, b2e);
+    p->cache->put(p->img.delta_rayleigh, b3);
+    p->cache->put(p->img.delta_mie, b3);
+    p->cache->put(p->img.scattering_density, b3);
+    p->cache->put(p->img.delta_multiple_scattering, b3);
+    p->cache->put(p->img.scratch, p->img.scratch_bytes);
     p->img.delta_irradiance = nullptr;
     p->img.delta_rayleigh = p->img.delta_mie = p->img.scattering_density = p->img.delta_multiple_scattering = nullptr;
     p->img.scratch = nullptr;
@@ -274,9 +343,9 @@ static void free_pending_temps(FbPending* p) {
 void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
     if (!a) return;
     DeviceGuard g(a->device);
-    cudaFree(a->transmittance);
-    cudaFree(a->irradiance);
-    cudaFree(a->scattering);
+    a->cache->put(a->transmittance, image_bytes(a->P, FB_IMAGE_TRANSMITTANCE));
+    a->cache->put(a->irradiance, image_bytes(a->P, FB_IMAGE_IRRADIANCE));
+    a->cache->put(a->scattering, image_bytes(a->P, FB_IMAGE_SCATTERING));
     delete a;
 }
 
@@ -301,6 +370,8 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     if (!p || !a) { delete p; delete a; return fail(FB_ERR_OUT_OF_MEMORY, "host allocation"); }
     std::memset(&p->img, 0, sizeof p->img);
     p->builder = b;
+    p->cache = b->cache;
+    a->cache = b->cache;
     p->P = *params;
     p->order = order;
     p->inner = a;
@@ -315,7 +386,7 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     const size_t b2t = image_bytes(*params, FB_IMAGE_TRANSMITTANCE), b2e = image_bytes(*params, FB_IMAGE_IRRADIANCE),
                  b3 = bytes3d(*params);
     cudaError_t e = cudaSuccess;
-    auto alloc = [&](void** ptr, size_t n) { if (e == cudaSuccess) e = cudaMalloc(ptr, n); };
+    auto alloc = [&](void** ptr, size_t n) { if (e == cudaSuccess) e = b->cache->get(ptr, n); };
     alloc((void**)&a->transmittance, b2t);
     alloc((void**)&a->irradiance, b2e);
     alloc((void**)&a->scattering, b3);

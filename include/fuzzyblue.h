@@ -146,6 +146,10 @@ FB_API int fb_params_validate(const FbParams* p);
 FB_API int fb_builder_create(int device, FbBuilder** out);
 FB_API void fb_builder_destroy(FbBuilder* b);
 FB_API int fb_builder_set_kernels(FbBuilder* b, int kernels /* FbKernels */);
+/* Device memory released by finished precomputes is cached (up to 8 GiB) for the next build of the same dims;
+ * fb_builder_trim returns the cached blocks to the driver.  Everything is released with the last object built from
+ * the builder. */
+FB_API int fb_builder_trim(FbBuilder* b);
 FB_API int fb_builder_device(const FbBuilder* b);
 FB_API int fb_builder_sm_count(const FbBuilder* b);
 /* Measured issue-rate ceilings of this device (dense FP32 FMA TFLOP/s, SFU Gop/s): the roofline

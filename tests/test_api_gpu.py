@@ -61,12 +61,20 @@ def test_pending_outlives_and_temporaries_are_freed():
     pend = fb.Atmosphere.build(b, None, fb.Parameters())
     sync()
     borrowed = pend.atmosphere().read_irradiance()
-    atm = pend.assert_ready()                        # frees the 5 temporaries (4 x 8 MiB + scratch), keeps the 3 tables
+    atm = pend.assert_ready()                        # releases the 5 temporaries (4 x 8 MiB + scratch) into the builder's cache
+    b.trim()                                         # ... and this returns the cache to the driver
     kept = free0 - torch.cuda.mem_get_info()[0]
     assert np.array_equal(atm.read_irradiance(), borrowed)
     assert kept <= 16 << 20, kept                    # 8 MiB scattering + 256 KiB + 16 KiB, allocator granularity
     atm.close()
+    b.trim()
     assert free0 - torch.cuda.mem_get_info()[0] <= 2 << 20
+    # a second build reuses the cached blocks of the first: same tables, no fresh allocation
+    p1 = fb.Atmosphere.build(b, None, fb.Parameters()); sync(); a1 = p1.assert_ready(); s1 = a1.read_scattering(); a1.close()
+    held = torch.cuda.mem_get_info()[0]
+    p2 = fb.Atmosphere.build(b, None, fb.Parameters()); sync()
+    assert torch.cuda.mem_get_info()[0] == held
+    assert np.array_equal(p2.assert_ready().read_scattering(), s1)
 
 
 def test_non_multiple_of_workgroup_dims_are_fully_written():
