@@ -207,6 +207,8 @@ struct FbAtmosphere {
     int device;
     int kernels;
     std::shared_ptr<BlockCache> cache;
+    void* block;             // one device block: [scattering | transmittance | irradiance]
+    size_t block_bytes;
     FbParams P;
     float4* transmittance;
     float4* irradiance;
@@ -216,6 +218,8 @@ struct FbAtmosphere {
 struct FbPending {
     FbBuilder* builder;
     std::shared_ptr<BlockCache> cache;
+    void* temp_block;        // one device block for the five temporaries and the kernel scratch
+    size_t temp_bytes;
     FbParams P;
     uint32_t order;
     Images img;
@@ -324,13 +328,8 @@ int fb_builder_device(const FbBuilder* b) { return b ? b->device : -1; }
 int fb_builder_sm_count(const FbBuilder* b) { return b ? b->sm_count : 0; }
 
 static void free_pending_temps(FbPending* p) {
-    const size_t b2e = image_bytes(p->P, FB_IMAGE_IRRADIANCE), b3 = bytes3d(p->P);
-    p->cache->put(p->img.delta_irradiance, b2e);
-    p->cache->put(p->img.delta_rayleigh, b3);
-    p->cache->put(p->img.delta_mie, b3);
-    p->cache->put(p->img.scattering_density, b3);
-    p->cache->put(p->img.delta_multiple_scattering, b3);
-    p->cache->put(p->img.scratch, p->img.scratch_bytes);
+    p->cache->put(p->temp_block, p->temp_bytes);
+    p->temp_block = nullptr;
     p->img.delta_irradiance = nullptr;
     p->img.delta_rayleigh = p->img.delta_mie = p->img.scattering_density = p->img.delta_multiple_scattering = nullptr;
     p->img.scratch = nullptr;
@@ -343,9 +342,7 @@ static void free_pending_temps(FbPending* p) {
 void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
     if (!a) return;
     DeviceGuard g(a->device);
-    a->cache->put(a->transmittance, image_bytes(a->P, FB_IMAGE_TRANSMITTANCE));
-    a->cache->put(a->irradiance, image_bytes(a->P, FB_IMAGE_IRRADIANCE));
-    a->cache->put(a->scattering, image_bytes(a->P, FB_IMAGE_SCATTERING));
+    a->cache->put(a->block, a->block_bytes);
     delete a;
 }
 
@@ -382,25 +379,32 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     a->kernels = b->kernels;
     a->P = *params;
     a->transmittance = nullptr; a->irradiance = nullptr; a->scattering = nullptr;
-    // one allocation per image, as the reference does (precompute.rs:1167-1234, :589-635)
-    const size_t b2t = image_bytes(*params, FB_IMAGE_TRANSMITTANCE), b2e = image_bytes(*params, FB_IMAGE_IRRADIANCE),
-                 b3 = bytes3d(*params);
-    cudaError_t e = cudaSuccess;
-    auto alloc = [&](void** ptr, size_t n) { if (e == cudaSuccess) e = b->cache->get(ptr, n); };
-    alloc((void**)&a->transmittance, b2t);
-    alloc((void**)&a->irradiance, b2e);
-    alloc((void**)&a->scattering, b3);
-    alloc((void**)&p->img.delta_irradiance, b2e);
-    alloc((void**)&p->img.delta_rayleigh, b3);
-    alloc((void**)&p->img.delta_mie, b3);
-    alloc((void**)&p->img.scattering_density, b3);
-    alloc((void**)&p->img.delta_multiple_scattering, b3);
+    a->block = nullptr; p->temp_block = nullptr;
+    // Two device blocks instead of the reference's one VkDeviceMemory per image (precompute.rs:1167-1234, :589-635):
+    // what the Atmosphere keeps, and what dies with the PendingAtmosphere.  Sub-allocations are 256-byte aligned.
+    auto up = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    const size_t b2t = up(image_bytes(*params, FB_IMAGE_TRANSMITTANCE)), b2e = up(image_bytes(*params, FB_IMAGE_IRRADIANCE)),
+                 b3 = up(bytes3d(*params));
     p->img.scratch_bytes = fast::scratch_bytes(*params);
-    if (p->img.scratch_bytes) alloc((void**)&p->img.scratch, p->img.scratch_bytes);
+    a->block_bytes = b3 + b2t + b2e;
+    p->temp_bytes = 4 * b3 + b2e + up(p->img.scratch_bytes);
+    cudaError_t e = b->cache->get(&a->block, a->block_bytes);
+    if (e == cudaSuccess) e = b->cache->get(&p->temp_block, p->temp_bytes);
     if (e != cudaSuccess) {
         fb_pending_destroy(p);
-        return cuda_fail(e, "cudaMalloc(image)");
+        return cuda_fail(e, "cudaMalloc(images)");
     }
+    char* kb = static_cast<char*>(a->block);
+    a->scattering = reinterpret_cast<uint2*>(kb);
+    a->transmittance = reinterpret_cast<float4*>(kb + b3);
+    a->irradiance = reinterpret_cast<float4*>(kb + b3 + b2t);
+    char* tb = static_cast<char*>(p->temp_block);
+    p->img.delta_rayleigh = reinterpret_cast<uint2*>(tb);
+    p->img.delta_mie = reinterpret_cast<uint2*>(tb + b3);
+    p->img.scattering_density = reinterpret_cast<uint2*>(tb + 2 * b3);
+    p->img.delta_multiple_scattering = reinterpret_cast<uint2*>(tb + 3 * b3);
+    p->img.delta_irradiance = reinterpret_cast<float4*>(tb + 4 * b3);
+    p->img.scratch = p->img.scratch_bytes ? reinterpret_cast<float*>(tb + 4 * b3 + b2e) : nullptr;
     p->img.transmittance = a->transmittance;
     p->img.irradiance = a->irradiance;
     p->img.scattering = a->scattering;
