@@ -88,9 +88,12 @@ def test_non_multiple_of_workgroup_dims_are_fully_written():
         assert np.all(np.isfinite(S.astype(np.float32))) and (S.astype(np.float32)[..., :3] > 0).mean() > 0.5
         assert np.all(np.isfinite(E)) and E.max() > 0
     from oracle import oracle as O
-    ref = O.precompute(O.Params(order=3, **dims), O.F32)
-    Tf, Sf, Ef = fb.precompute_host(fb.Builder(0), fb.Parameters(order=3, **dims))
-    assert np.max(np.abs(Tf - ref.transmittance) / ref.transmittance) <= 1e-3
-    assert np.max(np.abs(Ef - ref.irradiance) / np.maximum(ref.irradiance, 1e-30)) <= 1e-3
-    e = np.abs(Sf.astype(np.float64) - ref.scattering) / np.maximum(np.abs(ref.scattering), 2.0 ** -14)
-    assert (e > 1e-3).mean() <= 2e-3 and e.max() <= 2e-2
+    # second set: nu_size = 3 is not a power of two, so the product family's density stage falls back to the
+    # one-thread-per-texel kernel while every other stage stays on the fast path
+    for d in (dims, dict(dims, scattering_nu_size=3, scattering_mu_s_size=5)):
+        ref = O.precompute(O.Params(order=3, **d), O.F32)
+        Tf, Sf, Ef = fb.precompute_host(fb.Builder(0), fb.Parameters(order=3, **d))
+        assert np.max(np.abs(Tf - ref.transmittance) / ref.transmittance) <= 1e-3
+        assert np.max(np.abs(Ef - ref.irradiance) / np.maximum(ref.irradiance, 1e-30)) <= 1e-3
+        e = np.abs(Sf.astype(np.float64) - ref.scattering) / np.maximum(np.abs(ref.scattering), 2.0 ** -14)
+        assert (e > 1e-3).mean() <= 2e-3 and e.max() <= 2e-2, (d, e.max())
