@@ -111,7 +111,7 @@ typedef enum FbImage {
     FB_IMAGE_COUNT = 8
 } FbImage;
 
-/* The six compute shaders (shaders/*.comp) as individually launchable stages. */
+/* The six compute shaders (shaders/<name>.comp) as individually launchable stages. */
 typedef enum FbStage {
     FB_STAGE_TRANSMITTANCE = 0,       /* transmittance.comp:71-80 */
     FB_STAGE_DIRECT_IRRADIANCE = 1,   /* direct_irradiance.comp:36-46 */

@@ -76,3 +76,14 @@ def test_draw_parameters_are_column_major():
     flat = np.frombuffer(bytes(raw), dtype=np.float32)
     assert list(flat[:16]) == list(range(16)) and list(flat[16:19]) == [1, 2, 3] and list(flat[20:23]) == [4, 5, 6]
     assert np.array_equal(flat, O.pack_draw(cols, [1, 2, 3], [4, 5, 6]))
+
+
+def test_header_is_plain_c():
+    """include/fuzzyblue.h is the C ABI: it must compile as C99 with no C++ or CUDA headers."""
+    import subprocess
+    src = '#include "fuzzyblue.h"\nint main(void) { FbParams p; FbDrawParams d; return (int)(sizeof p + sizeof d) == 412 ? 0 : 1; }\n'
+    exe = os.path.join(ROOT, "tests", "c_header_check")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-x", "c", "-", "-o", exe],
+                   input=src.encode(), check=True)
+    assert subprocess.run([exe]).returncode == 0
+    os.remove(exe)

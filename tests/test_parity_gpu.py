@@ -316,6 +316,28 @@ def test_default_dims_against_golden(default_tables, family):
     print(f"scattering vs fp64 ideal: median {np.median(e):.2e} p99 {np.quantile(e, 0.99):.2e} max {e.max():.2e}")
 
 
+def test_default_dims_properties(default_tables):
+    """Size-independent properties at the full default dims (BASELINE.json configs[1])."""
+    T, E = default_tables["transmittance"], default_tables["irradiance"]
+    assert np.all((T[..., :3] > 0) & (T[..., :3] <= 1)) and np.all(T[..., 3] == 1)
+    assert np.all(T[-1, 0, :3] == 1)                                       # r = top, mu = 1: zero path length
+    assert np.all(np.diff(T[:, :, 0].astype(np.float64), axis=1) <= 1e-6)  # darker towards the horizon at every altitude
+    assert np.all(E >= 0) and np.all(E[..., 3] == 0)
+    prev = None
+    for name in ("o2_scattering", "o3_scattering", "scattering"):          # every order adds a non-negative term
+        S = default_tables[name].astype(np.float32)
+        assert np.all(np.isfinite(S)) and np.all(S >= 0)
+        if prev is not None:
+            assert np.all(S[..., :3] >= prev[..., :3]) and np.array_equal(S[..., 3], prev[..., 3])
+        prev = S
+    for order in (2, 3, 4):                                                # alpha channels of the temporaries (SURVEY §8c vii)
+        assert np.all(default_tables[f"o{order}_scattering_density"][..., 3] == 0)
+        assert np.all(default_tables[f"o{order}_delta_multiple_scattering"][..., 3] == 0)
+    # successive orders decay: the order-4 increment is smaller than the order-3 one, which is smaller than order 2's
+    inc = [float(default_tables[f"o{o}_delta_multiple_scattering"].astype(np.float64)[..., :3].sum()) for o in (2, 3, 4)]
+    assert inc[0] > inc[1] > inc[2] > 0
+
+
 def test_default_dims_stagewise_fast_vs_reference_family(family):
     """Default dims, every stage of the product kernels against the contraction-free transcription ON IDENTICAL INPUTS
     (the reference family's images are copied over before each stage), every texel of every output image: <= 1e-3."""

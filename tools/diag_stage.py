@@ -8,6 +8,12 @@ from fuzzyblue_b200 import api
 dims = {}
 if len(sys.argv) > 1 and sys.argv[1] == "dump":
     dims = dict(scattering_r_size=16, scattering_mu_size=64, scattering_mu_s_size=16, scattering_nu_size=4)
+if len(sys.argv) > 1 and sys.argv[1] == "hires2":   # half-scale cut of BASELINE.json configs[2]: rows of 1024 texels
+    dims = dict(scattering_r_size=16, scattering_mu_size=64, scattering_mu_s_size=64, scattering_nu_size=16,
+                transmittance_mu_size=512, transmittance_r_size=128)
+if len(sys.argv) > 1 and sys.argv[1] == "hires1":   # full-resolution rows (4096 texels), few r / mu
+    dims = dict(scattering_r_size=8, scattering_mu_size=16, scattering_mu_s_size=128, scattering_nu_size=32,
+                transmittance_mu_size=1024, transmittance_r_size=256)
 p = fb.Parameters(**dims)
 bR = fb.Builder(0, kernels=api.KERNELS_REFERENCE)
 bF = fb.Builder(0, kernels=api.KERNELS_FAST)
