@@ -7,7 +7,8 @@
 //
 // PARITY UNPINNED: the reference has no golden vectors, no known-answer tests and cannot be
 // built in this image (no cargo / shaderc / Vulkan ICD), so this file is pinned only by the
-// closed-form identities in tests/test_oracle_kat.py.
+// closed-form identities in tests/test_oracle_kat.py and cross-checked, stage by stage, against
+// an independent scalar numpy restatement of the same shaders (oracle/numpy_check.py, tests/test_oracle_numpy.py).
 //
 // Every routine restates one GLSL function of /root/reference/shaders (cited per function
 // as file:line) in a scalar type R chosen by the caller:
