@@ -285,3 +285,53 @@ def multiple_scattering_texel(a, T, dens, x, y, z):                     # multip
         mu_i, mu_s_i = clamp((r * mu + d) / r_i, -1.0, 1.0), clamp((r * mu_s + d * nu) / r_i, -1.0, 1.0)
         acc += scattering4(a, dens, r_i, mu_i, mu_s_i, nu, hits)[:3] * transmittance(a, T, r, mu, d, hits) * dx * (0.5 if i in (0, 50) else 1.0)
     return acc, nu
+
+
+# --- render_sky.h / render_sky.frag, one pixel ---------------------------------------------------------------------
+def extrapolated_single_mie(a, s):               # render_sky.h:9-19
+    if s[0] <= 0.0:
+        return np.zeros(3)
+    return s[:3] * s[3] / s[0] * (a.beta_r[0] / a.beta_m[0]) * (a.beta_m / a.beta_r)
+
+
+def sky_radiance_to_point(a, T, S, camera, view, point, sun):   # render_sky.h:111-191
+    camera, view, point, sun = (np.asarray(v, dtype=np.float64) for v in (camera, view, point, sun))
+    r = math.sqrt(float(camera @ camera))
+    rmu = float(camera @ view)
+    disc = rmu * rmu - r * r + a.top ** 2
+    to_top = -rmu - math.sqrt(disc) if disc >= 0 else float("nan")
+    if to_top > 0.0:
+        camera = camera + view * to_top
+        r = a.top
+        rmu += to_top
+    elif r > a.top:
+        return np.zeros(3), np.ones(3)
+    mu, mu_s, nu = rmu / r, float(camera @ sun) / r, float(view @ sun)
+    d = math.sqrt(float((point - camera) @ (point - camera)))
+    hits = hits_ground(a, r, mu)
+    tr = transmittance(a, T, r, mu, d, hits)
+    sc = scattering4(a, S, r, mu, mu_s, nu, hits)
+    mie = extrapolated_single_mie(a, sc)
+    sc = sc[:3]
+    if not math.isinf(d):
+        r_p = clamp(math.sqrt(d * d + 2.0 * r * mu * d + r * r), a.bottom, a.top)
+        mu_p, mu_s_p = (r * mu + d) / r_p, (r * mu_s + d * nu) / r_p
+        sp = scattering4(a, S, r_p, mu_p, mu_s_p, nu, hits)
+        mie_p = extrapolated_single_mie(a, sp)
+        sc = sc - tr * sp[:3]
+        mie = mie - tr * mie_p
+        mie = extrapolated_single_mie(a, np.array([sc[0], sc[1], sc[2], mie[0]]))
+        t = clamp(mu_s / 0.01, 0.0, 1.0)
+        mie = mie * (t * t * (3.0 - 2.0 * t))
+    return sc * rayleigh_phase(nu) + mie * mie_phase(a.g, nu), tr
+
+
+def render_pixel(a, T, S, draw23, depth, px, py, w, h):          # render_sky.frag:24-35, fullscreen.vert:5-8
+    M = np.asarray(draw23[:16], dtype=np.float64).reshape(4, 4).T   # columns are stored contiguously
+    cam, sun = np.asarray(draw23[16:19], dtype=np.float64), np.asarray(draw23[20:23], dtype=np.float64)
+    ndc = np.array([2.0 * (px + 0.5) / w - 1.0, 2.0 * (py + 0.5) / h - 1.0])
+    v = M @ np.array([ndc[0], ndc[1], 0.0, 1.0])
+    view = v[:3] / math.sqrt(float(v[:3] @ v[:3]))
+    wp = M @ np.array([ndc[0], ndc[1], float(depth), 1.0])
+    world = wp[:3] / wp[3] * 1e-3
+    return sky_radiance_to_point(a, T, S, cam, view, world, sun)

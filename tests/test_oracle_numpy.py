@@ -62,3 +62,23 @@ def test_multiple_scattering(tables):
         np.testing.assert_allclose(got, h["delta_multiple_scattering"][z, y, x, :3], rtol=RTOL, atol=1e-300)
         want = tables.history["single"]["scattering"][z, y, x, :3] + got / N.rayleigh_phase(nu)
         np.testing.assert_allclose(want, h["scattering"][z, y, x, :3], rtol=RTOL, atol=1e-300)
+
+
+def test_render_pixels(tables):
+    """render_sky.frag on a few geometry pixels of three views (ground below, at altitude, from space)."""
+    from fuzzyblue_b200 import synthetic
+    W, H = 32, 18
+    draws, extra = synthetic.camera_sweep(14, W, H)
+    checked = 0
+    for k in (1, 8, 13):
+        depth = synthetic.analytic_depth(extra[k][0], extra[k][1], W, H)
+        pd = O.pack_draw(draws[k].inverse_viewproj, draws[k].camera_position, draws[k].sun_direction)
+        oc, ot = O.render(P, O.F64, tables.transmittance, tables.scattering, pd, depth)
+        ys, xs = np.nonzero(depth > 0)
+        for j in range(0, len(ys), max(1, len(ys) // 6)):
+            c, t = N.render_pixel(A, tables.transmittance, tables.scattering, pd, depth[ys[j], xs[j]], xs[j], ys[j], W, H)
+            # the colour is a difference of nearly equal look-ups: compare at the scale of its operands
+            np.testing.assert_allclose(c, oc[ys[j], xs[j], :3], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(t, ot[ys[j], xs[j], :3], rtol=1e-7)
+            checked += 1
+    assert checked >= 12
