@@ -123,3 +123,25 @@ def test_library_queries(scene):
     torch.cuda.synchronize()
     assert close(direct.cpu().numpy(), od, 1e-6).all()
     assert close(sky.cpu().numpy(), osk, 1e-9).all()
+
+
+def test_4k_frame_properties(scene):
+    """BASELINE.json configs[4] frame size (3840x2160): size-independent properties of one ground-and-sky view —
+    finite outputs, transmittance in [0, 1], alpha channels, sky pixels unaffected by the depth of their neighbours,
+    and transmittance that can only grow when the ray is cut at the surface."""
+    W4, H4 = 3840, 2160
+    draws, extra = synthetic.camera_sweep(24, W4, H4)
+    k = 13                                                 # 121 km altitude, half ground / half sky
+    depth = synthetic.analytic_depth(extra[k][0], extra[k][1], W4, H4)
+    color, transm = scene["renderer"].draw_host(scene["atm"], draws[k], depth)
+    assert color.shape == (H4, W4, 4) and np.all(np.isfinite(color)) and np.all(np.isfinite(transm))
+    assert np.all(color[..., 3] == 0) and np.all(transm[..., 3] == 1)
+    assert np.all((transm[..., :3] >= 0) & (transm[..., :3] <= 1))
+    ground = depth > 0
+    assert 0.2 < ground.mean() < 0.8
+    assert color[~ground][:, :3].min() >= 0                # sky pixels: one look-up, no subtraction
+    # a sky pixel only depends on its own ray: blank out the ground and re-render
+    c2, t2 = scene["renderer"].draw_host(scene["atm"], draws[k], np.zeros_like(depth))
+    assert np.array_equal(c2[~ground], color[~ground]) and np.array_equal(t2[~ground], transm[~ground])
+    # ground pixels got darker / unchanged transmittance-wise when the ray is cut at the surface
+    assert np.all(transm[ground][:, :3] >= t2[ground][:, :3] - 1e-6)
