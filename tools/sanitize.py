@@ -1,0 +1,25 @@
+"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck): reduced, odd and wide dims, both orders' density
+variants, the renderer and the library queries."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import fuzzyblue_b200 as fb
+from fuzzyblue_b200 import api, synthetic
+b = fb.Builder(0)
+cases = [dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=8, scattering_nu_size=2, order=3),
+         dict(scattering_r_size=2, scattering_mu_size=4, scattering_mu_s_size=64, scattering_nu_size=32, order=3),
+         dict(scattering_r_size=3, scattering_mu_size=6, scattering_mu_s_size=5, scattering_nu_size=4, order=3,
+              transmittance_mu_size=37, transmittance_r_size=11, irradiance_mu_s_size=13, irradiance_r_size=5)]
+for d in cases:
+    T, S, E = fb.precompute_host(b, fb.Parameters(**d))
+    assert np.isfinite(S.astype(np.float32)).all() and np.isfinite(E).all()
+p = fb.Parameters(**cases[0])
+pend = fb.Atmosphere.build(b, None, p); torch.cuda.synchronize()
+pend.resubmit(None); torch.cuda.synchronize()
+atm = pend.assert_ready()
+r = fb.Renderer(b)
+draws, extra = synthetic.camera_sweep(14, 64, 36)
+for k in (1, 2, 13):
+    c, t = r.draw_host(atm, draws[k], synthetic.analytic_depth(extra[k][0], extra[k][1], 64, 36))
+    assert np.isfinite(c).all()
+print("sanitize pass done")
