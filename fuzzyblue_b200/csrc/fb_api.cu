@@ -233,7 +233,7 @@ struct FbPending {
 struct FbRenderer {
     int device;
     int kernels;
-    FbDrawParams* sweep_draws;   // device copy of a sweep's draw parameters
+    void* sweep_draws;           // device copy of a sweep's draw parameters + per-view constants
     uint32_t sweep_capacity;
 };
 
@@ -712,20 +712,15 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
     if (r->device != a->device) return fail(FB_ERR_INVALID_ARGUMENT, "draw: renderer and atmosphere live on different devices");
     if (h > 65535 || views > 65535) return fail(FB_ERR_INVALID_ARGUMENT, "draw: height / views exceed the launch grid");
     DeviceGuard g(r->device);
-    const FbDrawParams* dev = nullptr;
-    if (views > 1) {
-        if (views > r->sweep_capacity) {
-            cudaFree(r->sweep_draws);
-            r->sweep_draws = nullptr;
-            r->sweep_capacity = 0;
-            FB_CUDA(cudaMalloc((void**)&r->sweep_draws, (size_t)views * sizeof(FbDrawParams)));
-            r->sweep_capacity = views;
-        }
-        FB_CUDA(cudaMemcpyAsync(r->sweep_draws, d, (size_t)views * sizeof(FbDrawParams), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-        dev = r->sweep_draws;
+    if (views > 1 && views > r->sweep_capacity) {
+        cudaFree(r->sweep_draws);
+        r->sweep_draws = nullptr;
+        r->sweep_capacity = 0;
+        FB_CUDA(cudaMalloc(&r->sweep_draws, (size_t)views * render_view_record_bytes()));
+        r->sweep_capacity = views;
     }
-    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, d[0], dev, views, depth, (float4*)color, (float4*)transm,
-                               (float4*)blend, w, h, r->kernels, (cudaStream_t)stream);
+    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, d, views > 1 ? r->sweep_draws : nullptr, views, depth,
+                               (float4*)color, (float4*)transm, (float4*)blend, w, h, r->kernels, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_sky launch");
     return FB_OK;
 }

@@ -37,13 +37,16 @@ def _reverse_z_infinite(vfov: float, aspect: float, near: float) -> np.ndarray:
     return p
 
 
-def camera_sweep(n_views: int, width: int, height: int, bottom_radius_km: float = 6360.0, seed: int = 4):
+def camera_sweep(n_views: int, width: int, height: int, bottom_radius_km: float = 6360.0, seed: int = 4, altitudes_km=None):
     """`n_views` cameras: altitude log-uniform 1 m .. 2000 km, yaw U[0,2pi), pitch U[-60,60] deg, vfov 60 deg,
-    sun zenith angle U[0,110] deg.  Returns (list[DrawParameters], list[(M_inv float64, eye_m float64)])."""
+    sun zenith angle U[0,110] deg (`altitudes_km`, if given, replaces the random altitudes).
+    Returns (list[DrawParameters], list[(M_inv float64, eye_m float64)])."""
     rng = np.random.default_rng(seed)
     draws, extra = [], []
-    for _ in range(n_views):
+    for k in range(n_views):
         alt_km = math.exp(rng.uniform(math.log(1e-3), math.log(2000.0)))
+        if altitudes_km is not None:
+            alt_km = float(altitudes_km[k])
         yaw, pitch = rng.uniform(0, 2 * math.pi), math.radians(rng.uniform(-60, 60))
         eye_km = np.array([0.0, 0.0, bottom_radius_km + alt_km])
         fwd = np.array([math.cos(pitch) * math.cos(yaw), math.cos(pitch) * math.sin(yaw), math.sin(pitch)])

@@ -145,3 +145,48 @@ def test_4k_frame_properties(scene):
     assert np.array_equal(c2[~ground], color[~ground]) and np.array_equal(t2[~ground], transm[~ground])
     # ground pixels got darker / unchanged transmittance-wise when the ray is cut at the surface
     assert np.all(transm[ground][:, :3] >= t2[ground][:, :3] - 1e-6)
+
+
+def test_fast_family_hoisting_is_exact():
+    """The FAST kernel evaluates parameter-only and camera-only sub-expressions once on the host; every texture
+    coordinate must still be the one the contraction-free kernel derives per pixel, so the two families agree to the
+    rounding of the convex blends (measured 4e-7) on the same tables -- including cameras at / around the top boundary,
+    where the per-view constants must not be used (render_sky.h:121-131), under ground and in space."""
+    import copy
+    import torch
+    bF, bR = fb.Builder(0), fb.Builder(0, kernels=api.KERNELS_REFERENCE)
+    pend = fb.Atmosphere.build(bF, None, fb.Parameters(**DUMP_DIMS))
+    torch.cuda.synchronize()
+    atm = pend.atmosphere()
+    rF, rR = fb.Renderer(bF), fb.Renderer(bR)
+    views = []
+    alts = (59.0, 59.67, 59.69, 59.99, 60.0, 60.001, 61.0, 1e-4, 3.0)          # km above the ground; top = +60 km
+    for seed, altitudes in ((11, None), (12, alts)):
+        draws, extra = synthetic.camera_sweep(16 if altitudes is None else len(alts), W, H, seed=seed, altitudes_km=altitudes)
+        for d, (inv, eye) in zip(draws, extra):
+            views.append((d, synthetic.analytic_depth(inv, eye, W, H)))
+    under = copy.deepcopy(views[0][0])                                         # a camera below the surface: rho = 0
+    under.camera_position = [0.0, 0.0, 6359.5]
+    views.append((under, views[0][1]))
+    worst = 0.0
+    for d, depth in views:
+        cF, tF = rF.draw_host(atm, d, depth)
+        cR, tR = rR.draw_host(atm, d, depth)
+        ok = np.isfinite(cR).all(axis=-1) & np.isfinite(tR).all(axis=-1)
+        assert np.array_equal(np.isfinite(cF), np.isfinite(cR)) and np.array_equal(np.isfinite(tF), np.isfinite(tR))
+        peak = max(float(np.abs(cR[ok]).max()), 1e-3)
+        ec = np.abs(cF - cR)[ok] / np.maximum(np.abs(cR[ok]), 1e-3 * peak)
+        et = np.abs(tF - tR)[ok] / np.maximum(np.abs(tR[ok]), 1e-6)
+        worst = max(worst, float(ec.max()), float(et.max()))
+    assert worst < 5e-6, worst
+    # a sweep reads the per-view records from device memory, a single draw from kernel parameters: same bits
+    n = len(views)
+    depth = torch.from_numpy(np.stack([v[1] for v in views])).cuda()
+    color = torch.empty((n, H, W, 4), device="cuda")
+    transm = torch.empty((n, H, W, 4), device="cuda")
+    rF.draw_sweep(None, atm, [v[0] for v in views], depth, color, transm, W, H)
+    torch.cuda.synchronize()
+    for k in (0, 16, 17, 18, 20, 21, n - 1):
+        c1, t1 = rF.draw_host(atm, views[k][0], views[k][1])
+        assert np.array_equal(color[k].cpu().numpy(), c1, equal_nan=True)
+        assert np.array_equal(transm[k].cpu().numpy(), t1, equal_nan=True)
