@@ -10,6 +10,8 @@
 //   * only convex interpolation, phase functions and the accumulation of positive terms run in plain
 //     fp32 with FMA contraction and a different summation order (relative effect ~1e-7).
 #include "fb_kernels.h"
+
+#include <type_traits>
 #include "fb_shader_math.cuh"
 
 namespace fb {
@@ -110,31 +112,31 @@ static inline DensityDims density_dims(const FbParams& P, int T) {
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
     return d;
 }
-// scratch: table [R][tiles][DL][T][ENT] floats (sized for the order-2 layout, the larger one) + ground [R][DL][2] float4
-// + a snapshot of row 0 of delta_irradiance (so that indirect_irradiance may overwrite the image while the main kernel runs)
+// scratch: table [R][tiles][DL][T][ENT] floats (sized for the order-2 layout, the larger one) + ground normals
+// [R][DL] float4 + ground rows [R][DL/2][nE][3] float2: row 0 of delta_irradiance as (value, delta) pairs, multiplied
+// by the ground factor of (r, theta_l) for the eight downward theta rows (the others cannot reach the ground)
 static inline size_t density_tab_floats(const FbParams& P) {
     DensityDims d = density_dims(P, DensityCfg<true>::T);
     return (size_t)P.scattering_r_size * d.tiles * DL * DensityCfg<true>::T * DensityCfg<true>::ENT;
 }
+static inline size_t density_grow_floats(const FbParams& P) { return (size_t)P.scattering_r_size * (DL / 2) * P.irradiance_mu_s_size * 6; }
 
 size_t scratch_bytes(const FbParams& P) {
     if (!density_supported(P)) return 0;
-    return density_tab_floats(P) * sizeof(float) + ((size_t)P.scattering_r_size * DL * 2 + P.irradiance_mu_s_size) * sizeof(float4);
+    return (density_tab_floats(P) + density_grow_floats(P)) * sizeof(float) + (size_t)P.scattering_r_size * DL * sizeof(float4);
 }
 
 template <bool ORDER2>
 __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
                                                       Tex3 A0, Tex3 A1, DensityDims dd, float* __restrict__ tab,
                                                       float4* __restrict__ gnd, const float4* __restrict__ dE_row0,
-                                                      float4* __restrict__ erow_snapshot, int r0) {
+                                                      float2* __restrict__ grow, int r0) {
     constexpr int ENT = DensityCfg<ORDER2>::ENT, TT = DensityCfg<ORDER2>::T;
     const int l = blockIdx.y, z = r0 + blockIdx.z;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)   // GetIrradiance(bottom, .) only ever reads row 0
-        for (int i = threadIdx.x; i < P.irradiance_mu_s_size; i += blockDim.x) erow_snapshot[i] = dE_row0[i];
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    if (e >= W) return;
-    const int k = e % dd.nu, ms = e / dd.nu;
+    const bool active = e < W;
+    const int k = e % dd.nu, ms = active ? e / dd.nu : 0;
     A<F> a(P);
     F r, mu_unused, mu_s, nu_unused;
     bool hits_unused;
@@ -142,6 +144,32 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
     a.TexelToRMuMuSNu((unsigned)ms, 0u, (unsigned)z, r, mu_unused, mu_s, nu_unused, hits_unused);
     const F ct = F(tg.ct16[l]), st = F(tg.st16[l]);
     const bool hits = a.RayIntersectsGround(r, ct);                                   // scattering_density.comp:45-46
+    if (blockIdx.x == 0) {   // per-(r, theta) ground terms, scattering_density.comp:50-60, :81-87 (the whole block: r is uniform)
+        float gx = 0.f, gy = 0.f, gz = 0.f, nx = 0.f, nz = 0.f;
+        if (hits) {
+            F dg = a.DistanceToBottom(r, ct);
+            V tgr = a.Transmittance(T, r, ct, dg, true);
+            V G = tgr * V(P.ground_albedo) * (F(1.f) / F(FB_PI_F));
+            // ground_normal = normalize(zenith*r + w_i*dg); its length does not depend on phi:
+            // (st*dg)^2 + (r + ct*dg)^2, so dot(normal, w_s) = q*(st*dg/len) + mu_s*((r + ct*dg)/len)
+            // with q = sx cos(phi) + sy sin(phi)
+            F vx = st * dg, vz = r + ct * dg;
+            F len = f_sqrt(vx * vx + vz * vz);
+            gx = G.x.v; gy = G.y.v; gz = G.z.v; nx = (vx / len).v; nz = (vz / len).v;
+        }
+        if (threadIdx.x == 0) gnd[(size_t)z * DL + l] = make_float4(nx, nz, hits ? 1.f : 0.f, 0.f);
+        if (l >= DL / 2) {   // GetIrradiance(bottom, .) only ever reads row 0 of delta_irradiance (irradiance.h:20-30)
+            const int nE = P.irradiance_mu_s_size;
+            float2* o = grow + ((size_t)z * (DL / 2) + (l - DL / 2)) * nE * 3;
+            for (int i = threadIdx.x; i < nE; i += blockDim.x) {
+                const float4 v0 = __ldg(dE_row0 + i), v1 = __ldg(dE_row0 + min(i + 1, nE - 1));
+                o[i * 3] = make_float2(gx * v0.x, gx * (v1.x - v0.x));
+                o[i * 3 + 1] = make_float2(gy * v0.y, gy * (v1.y - v0.y));
+                o[i * 3 + 2] = make_float2(gz * v0.z, gz * (v1.z - v0.z));
+            }
+        }
+    }
+    if (!active) return;
     F uvwz[4];
     a.ScatteringUvwz(r, ct, mu_s, F(0.f), hits, uvwz);                                // scattering.h:144-145
     const F nn = F((float)dd.nu);
@@ -164,23 +192,6 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
         o2[0] = make_float2(s0.x.v, s1.x.v - s0.x.v);
         o2[1] = make_float2(s0.y.v, s1.y.v - s0.y.v);
         o2[2] = make_float2(s0.z.v, s1.z.v - s0.z.v);
-    }
-    if (e == 0) {   // per-(r, theta) ground constants, scattering_density.comp:50-60, :81-87
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-        if (hits) {
-            F dg = a.DistanceToBottom(r, ct);
-            V tgr = a.Transmittance(T, r, ct, dg, true);
-            V G = tgr * V(P.ground_albedo) * (F(1.f) / F(FB_PI_F));
-            // ground_normal = normalize(zenith*r + w_i*dg); its length does not depend on phi:
-            // (st*dg)^2 + (r + ct*dg)^2, so dot(normal, w_s) = q*(st*dg/len) + mu_s*((r + ct*dg)/len)
-            // with q = sx cos(phi) + sy sin(phi)
-            F vx = st * dg, vz = r + ct * dg;
-            F len = f_sqrt(vx * vx + vz * vz);
-            g0 = make_float4(G.x.v, G.y.v, G.z.v, (vx / len).v);
-            g1 = make_float4((vz / len).v, 1.f, 0.f, 0.f);
-        }
-        gnd[((size_t)z * DL + l) * 2] = g0;
-        gnd[((size_t)z * DL + l) * 2 + 1] = g1;
     }
 }
 
@@ -208,30 +219,28 @@ __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; caller
 template <bool ORDER2>
 __global__ void __launch_bounds__(256, 2)
 k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float* __restrict__ tabG,
-               const float4* __restrict__ gndG, const float4* __restrict__ dE_row0, uint2* __restrict__ out, int r0,
+               const float4* __restrict__ gndG, const float2* __restrict__ growG, uint2* __restrict__ out, int r0,
                uint32_t magic_tab, uint32_t magic_row) {
     typedef DensityCfg<ORDER2> C;
     constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
     constexpr int ENT_B = ENT * 4;                       // bytes per table entry
     constexpr int L_STRIDE = TT * ENT_B;                 // bytes per theta row block
     constexpr int TAB_B = DL * L_STRIDE;                 // 96 KiB
-    // shared memory map (bytes): [table TAB_B][geo TT*16][Wt DL*32*16, later reused as outS TT*16][gnd DL*32][Erow nE*24][mbar 8]
-    constexpr int GEO_OFF = TAB_B, WT_OFF = GEO_OFF + TT * 16, GND_OFF = WT_OFF + DL * 32 * 16, EROW_OFF = GND_OFF + DL * 32;
-    static_assert(TT * 16 <= DL * 32 * 16, "outS aliases WtS");
+    // shared memory map (bytes): [table TAB_B][geo TT*16][ground normals DL*8][2 mbarriers, padded to 128]
+    //                            [Wt DL*32*16 during the prologue, then the 8 ground rows (DL/2)*nE*24]
+    constexpr int GEO_OFF = TAB_B, NXZ_OFF = GEO_OFF + TT * 16, BAR_OFF = NXZ_OFF + DL * 8, GR_OFF = BAR_OFF + 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* geoS = reinterpret_cast<float4*>(smem_raw + GEO_OFF);
-    float4* WtS = reinterpret_cast<float4*>(smem_raw + WT_OFF);
-    float4* outS = WtS;
-    float4* gndS = reinterpret_cast<float4*>(smem_raw + GND_OFF);
-    float2* ErowS = reinterpret_cast<float2*>(smem_raw + EROW_OFF);
+    float2* nxzS = reinterpret_cast<float2*>(smem_raw + NXZ_OFF);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + BAR_OFF);
+    float4* WtS = reinterpret_cast<float4*>(smem_raw + GR_OFF);
     const int nE = P.irradiance_mu_s_size;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + EROW_OFF + nE * 24);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
 
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, TAB_B);
@@ -278,12 +287,11 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             WtS[e] = make_float4(w.x.v, w.y.v, w.z.v, 0.f);
         }
     }
-    for (int e = tid; e < DL * 2; e += NWARPS * 32) gndS[e] = __ldg(gndG + (size_t)z * DL * 2 + e);
-    for (int e = tid; e < nE; e += NWARPS * 32) {   // row 0 of delta_irradiance as (value, delta) pairs
-        const float4 v0 = __ldg(dE_row0 + e), v1 = __ldg(dE_row0 + min(e + 1, nE - 1));
-        ErowS[e * 3] = make_float2(v0.x, v1.x - v0.x);
-        ErowS[e * 3 + 1] = make_float2(v0.y, v1.y - v0.y);
-        ErowS[e * 3 + 2] = make_float2(v0.z, v1.z - v0.z);
+    uint32_t gmask = 0;                                                        // theta rows that reach the ground (CTA-uniform)
+    for (int l = DL / 2; l < DL; ++l) {
+        const float4 g = __ldg(gndG + (size_t)z * DL + l);
+        if (g.z != 0.f) gmask |= 1u << l;
+        if (tid == l) nxzS[l] = make_float2(g.x, g.y);
     }
     __syncthreads();
 
@@ -294,9 +302,13 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         const float4 w = WtS[l * 32 + lane];
         Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
     }
-    uint32_t gmask = 0;
-    for (int l = 0; l < DL; ++l)
-        if (gndS[l * 2 + 1].y != 0.f) gmask |= 1u << l;
+    __syncthreads();                          // every warp holds its weights: their region now receives the ground rows
+    const uint32_t grow_b = (uint32_t)nE * 24u;                                // bytes per ground row
+    if (gmask && tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic reads above, async-proxy writes below
+        mbar_expect_tx(bar + 1, (DL / 2) * grow_b);
+        tma_bulk_g2s(smem_raw + GR_OFF, growG + (size_t)z * (DL / 2) * nE * 3, (DL / 2) * grow_b, bar + 1);
+    }
     const float cp = tg.cp32[lane], sp = tg.sp32[lane];
     const float hn = 0.5f * (float)(dd.nu - 1);
     const float MAGIC = 8388608.f;   // 2^23: x + MAGIC rounded down leaves floor(x) in the low mantissa bits
@@ -317,11 +329,18 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     asm volatile("" : "+r"(sbase));           // one register for every region; offsets below are immediates
     const uint32_t tab_base = sbase - magic_tab;
     const uint32_t erow_t = sbase - magic_row;
-    __syncthreads();                          // every warp holds its weights: WtS may now be reused as outS
+    const int out_row = (z * P.scattering_mu_size + y) * W;
 
     mbar_wait(bar, 0);
+    if (gmask) mbar_wait(bar + 1, 0);
 
     // ---- one warp per texel, lane = phi sample -------------------------------------------------------------
+    // The theta rows that reach the ground are a suffix l >= L0 of the downward rows (a steeper ray hits if a shallower
+    // one does).  The two patterns an Earth-like shell produces are compiled with L0 fixed: the 16 unrolled steps then
+    // form one basic block and the loads of later steps are scheduled across the ground terms of earlier ones.  Any
+    // other pattern takes the L0 = -1 body, which tests the mask per step.
+    auto texels = [&](auto L0c) __attribute__((always_inline)) {
+    constexpr int L0 = decltype(L0c)::value;
     for (int t = warp; t < TT; t += NWARPS) {
         const float4 geo = geoS[t];
         if (__float_as_int(geo.w) < 0) continue;                                  // padding texel of a partial tile
@@ -358,18 +377,17 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                              cb = lds64<(l) * L_STRIDE + 16>(addr);                                                     \
                 Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);                           \
             }                                                                                                           \
-            if (gmask & (1u << (l))) {                                            /* warp-uniform */                    \
-                const float4 G = lds128<GND_OFF + (l) * 32>(sbase);               /* (G.rgb, n_x) */                    \
-                const float gz = lds32<GND_OFF + (l) * 32 + 16>(sbase);                                                 \
-                const float musg = fmaf(q, G.w, mus * gz);                        /* dot(ground_normal, omega_s) */     \
+            if (L0 >= 0 ? (l) >= L0 : ((l) >= DL / 2 && (gmask & (1u << (l))) != 0)) {  /* CTA-uniform */              \
+                const float2 N = lds64<NXZ_OFF + (l) * 8>(sbase);                 /* ground normal: (n_x, n_z) */       \
+                const float musg = fmaf(q, N.x, mus * N.y);                       /* dot(ground_normal, omega_s) */     \
                 const float te = fmaf(musg, e_c, e_c);                            /* irradiance.h:20-30, r = bottom */  \
                 const float em = __fadd_rd(te, MAGIC);                                                                  \
                 const float fe = te - (em - MAGIC);                                                                     \
-                const uint32_t ea = erow_t + __float_as_uint(em) * 24u;                                                 \
-                const float2 er = lds64<EROW_OFF>(ea), eg = lds64<EROW_OFF + 8>(ea), eb = lds64<EROW_OFF + 16>(ea);     \
-                Lr = fmaf(G.x, fmaf(fe, er.y, er.x), Lr);                                                               \
-                Lg = fmaf(G.y, fmaf(fe, eg.y, eg.x), Lg);                                                               \
-                Lb = fmaf(G.z, fmaf(fe, eb.y, eb.x), Lb);                                                               \
+                const uint32_t ea = erow_t + (uint32_t)((l) - DL / 2) * grow_b + __float_as_uint(em) * 24u;             \
+                const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);           \
+                Lr += fmaf(fe, er.y, er.x);                                       /* rows carry the ground factor */    \
+                Lg += fmaf(fe, eg.y, eg.x);                                                                             \
+                Lb += fmaf(fe, eb.y, eb.x);                                                                             \
             }                                                                                                           \
             ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);                               \
         }
@@ -384,21 +402,21 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             ag += __shfl_xor_sync(0xffffffffu, ag, s);
             ab += __shfl_xor_sync(0xffffffffu, ab, s);
         }
-        if (lane == 0) outS[t] = make_float4(ar, ag, ab, 0.f);
-    }
-    __syncthreads();
-    for (int t = tid; t < TT; t += NWARPS * 32) {
-        const int nui = t / dd.ms_tile, ms = tile * dd.ms_tile + t % dd.ms_tile;
-        if (ms < P.scattering_mu_s_size) {
-            const float4 v = outS[t];
-            out[((size_t)z * P.scattering_mu_size + y) * W + nui * P.scattering_mu_s_size + ms] = pack_half4(v.x, v.y, v.z, 0.f);
+        if (lane == 0) {
+            const int nui = t / dd.ms_tile, ms = tile * dd.ms_tile + t % dd.ms_tile;
+            out[out_row + nui * P.scattering_mu_s_size + ms] = pack_half4(ar, ag, ab, 0.f);
         }
     }
+    };
+    if (gmask == 0xFF00u) texels(std::integral_constant<int, 8>());
+    else if (gmask == 0xFE00u) texels(std::integral_constant<int, 9>());
+    else texels(std::integral_constant<int, -1>());
 }
 
 template <bool ORDER2> static size_t density_smem(const FbParams& P) {
     typedef DensityCfg<ORDER2> C;
-    return (size_t)DL * C::T * C::ENT * 4 + C::T * 16 + DL * 32 * 16 + DL * 32 + (size_t)P.irradiance_mu_s_size * 24 + 16;
+    const size_t wt = (size_t)DL * 32 * 16, gr = (size_t)(DL / 2) * P.irradiance_mu_s_size * 24;
+    return (size_t)DL * C::T * C::ENT * 4 + C::T * 16 + DL * 8 + 128 + (wt > gr ? wt : gr);
 }
 
 template <bool ORDER2>
@@ -408,19 +426,19 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     const DensityDims d = density_dims(P, C::T);
     const size_t smem = density_smem<ORDER2>(P);
     float* tab = c.img.scratch;
-    float4* gnd = reinterpret_cast<float4*>(tab + density_tab_floats(P));
+    float2* grow = reinterpret_cast<float2*>(tab + density_tab_floats(P));
+    float4* gnd = reinterpret_cast<float4*>(tab + density_tab_floats(P) + density_grow_floats(P));
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     dim3 gp((W + 255) / 256, DL, r1 - r0);
     dim3 gm(d.tiles, P.scattering_mu_size, r1 - r0);
-    float4* erow = gnd + (size_t)P.scattering_r_size * DL * 2;
-    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, gnd, c.img.delta_irradiance, erow, r0);
+    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, gnd, c.img.delta_irradiance, grow, r0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // from here on nothing reads delta_irradiance: indirect_irradiance may run concurrently with the main kernel
     if (after_prep && (e = cudaEventRecord(after_prep, c.stream)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, erow,
+    k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, grow,
                                                                   c.img.scattering_density, r0,
                                                                   0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u);
     return cudaGetLastError();
@@ -678,6 +696,7 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scatte
     // per-texel constants of the 4-D look-up: the nu slice pair (scattering.h:146-152) and the sun-angle terms
     float ln[TPT], rmus[TPT], nuf[TPT], ar[TPT], ag[TPT], ab[TPT];
     int kx0[TPT], kx1[TPT];
+    bool two[TPT];       // this texel interpolates between two nu slices (scattering.h:150-154)
     F r, mu;
     bool hits;
 #pragma unroll
@@ -692,6 +711,10 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scatte
         kx0[k] = tx * MS; kx1[k] = min(tx + 1, NU - 1) * MS;
         rmus[k] = (r * mu_s).v; nuf[k] = nu.v;
         ar[k] = ag[k] = ab[k] = 0.f;
+        // a texel whose nu was not clamped sits on a nu knot: lerp == 0 exactly and fma(0, v1 - v0, v0) == v0, so the
+        // second slice need not be fetched (bit-identical; 65 % of the texels at default dims, but every warp holds
+        // a clamped lane -- mu_s = 1 admits a single nu -- so this is predication, not a uniform branch)
+        two[k] = ln[k] != 0.f;
     }
     for (int i = threadIdx.x; i < NS; i += blockDim.x) {
         const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);                        // multiple_scattering.comp:23-26
@@ -750,27 +773,34 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scatte
 #pragma unroll
         for (int k = 0; k < TPT; ++k) {
             if ((int)(threadIdx.x + k * blockDim.x) < W) {
-#pragma unroll 4
-                for (int e = 0; e < cn; ++e) {
-                    const float4 nt = nodes[c0 + e].t;
-                    const float inv_r = nodes[c0 + e].inv_r;
-                    const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf[k], rmus[k]) * inv_r, -1.f), 1.f);   // :38
-                    // DistanceToTopAtmosphereBoundary(bottom, mu_s_i), params.h:105-110: b^2 (mu^2 - 1) + top^2 > 0 always
-                    const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));
-                    const float aa = (dd - dmin) * inv_span;
-                    const float xx = fmaxf(fmaf(aa, minvA, 1.f), 0.f) * rcp_fast(1.f + aa);   // 1 + a is in [1, 2]
-                    const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);
-                    const float tm = __fadd_rd(t, 8388608.f);
-                    const int j = __float_as_int(tm) - 0x4B000000;
-                    const float fx = t - (tm - 8388608.f);
-                    const float4* s = slab + e * W + j;
-                    const float4 p00 = s[kx0[k]], p01 = s[kx0[k] + 1], p10 = s[kx1[k]], p11 = s[kx1[k] + 1];
-                    const float v0r = fmaf(fx, p01.x - p00.x, p00.x), v0g = fmaf(fx, p01.y - p00.y, p00.y), v0b = fmaf(fx, p01.z - p00.z, p00.z);
-                    const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z);
-                    ar[k] = fmaf(fmaf(ln[k], v1r - v0r, v0r), nt.x, ar[k]);
-                    ag[k] = fmaf(fmaf(ln[k], v1g - v0g, v0g), nt.y, ag[k]);
-                    ab[k] = fmaf(fmaf(ln[k], v1b - v0b, v0b), nt.z, ab[k]);
+#define FB_MS_SAMPLE(TWO)                                                                                                   \
+                for (int e = 0; e < cn; ++e) {                                                                              \
+                    const float4 nt = nodes[c0 + e].t;                                                                      \
+                    const float inv_r = nodes[c0 + e].inv_r;                                                                \
+                    const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf[k], rmus[k]) * inv_r, -1.f), 1.f);   /* :38 */           \
+                    /* DistanceToTopAtmosphereBoundary(bottom, mu_s_i), params.h:105-110: b^2 (mu^2 - 1) + top^2 > 0 */     \
+                    const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));                             \
+                    const float aa = (dd - dmin) * inv_span;                                                                \
+                    const float xx = fmaxf(fmaf(aa, minvA, 1.f), 0.f) * rcp_fast(1.f + aa);   /* 1 + a is in [1, 2] */      \
+                    const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);                                                     \
+                    const float tm = __fadd_rd(t, 8388608.f);                                                               \
+                    const int j = __float_as_int(tm) - 0x4B000000;                                                          \
+                    const float fx = t - (tm - 8388608.f);                                                                  \
+                    const float4* s = slab + e * W + j;                                                                     \
+                    const float4 p00 = s[kx0[k]], p01 = s[kx0[k] + 1];                                                      \
+                    float vr = fmaf(fx, p01.x - p00.x, p00.x), vg = fmaf(fx, p01.y - p00.y, p00.y), vb = fmaf(fx, p01.z - p00.z, p00.z); \
+                    if (TWO) {                                                                                              \
+                        const float4 p10 = s[kx1[k]], p11 = s[kx1[k] + 1];                                                  \
+                        const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z); \
+                        vr = fmaf(ln[k], v1r - vr, vr); vg = fmaf(ln[k], v1g - vg, vg); vb = fmaf(ln[k], v1b - vb, vb);     \
+                    }                                                                                                       \
+                    ar[k] = fmaf(vr, nt.x, ar[k]);                                                                          \
+                    ag[k] = fmaf(vg, nt.y, ag[k]);                                                                          \
+                    ab[k] = fmaf(vb, nt.z, ab[k]);                                                                          \
                 }
+#pragma unroll 4
+                FB_MS_SAMPLE(two[k])
+#undef FB_MS_SAMPLE
             }
         }
     }
