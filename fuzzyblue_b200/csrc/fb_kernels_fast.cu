@@ -341,6 +341,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     // other pattern takes the L0 = -1 body, which tests the mask per step.
     auto texels = [&](auto L0c) __attribute__((always_inline)) {
     constexpr int L0 = decltype(L0c)::value;
+#pragma unroll 2
     for (int t = warp; t < TT; t += NWARPS) {
         const float4 geo = geoS[t];
         if (__float_as_int(geo.w) < 0) continue;                                  // padding texel of a partial tile
