@@ -447,7 +447,7 @@ static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order
             break;
         default: return fail(FB_ERR_INVALID_ARGUMENT, "unknown stage");
     }
-    if (fastk && stage <= FB_STAGE_MULTIPLE_SCATTERING) n = fast::launches_per_stage(stage);
+    if (fastk && stage <= FB_STAGE_MULTIPLE_SCATTERING) n = fast::launches_per_stage(c.P, stage, r1 - r0);
     if (e != cudaSuccess) return cuda_fail(e, (std::string("stage ") + std::to_string(stage) + " launch").c_str());
     if (launches) *launches += n;
     return FB_OK;
@@ -480,7 +480,7 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
             // overwrites the delta_multiple_scattering K5 reads).
             cudaError_t e = fast::scattering_density(c, (int)order, 0, R, p->ev_fork);
             if (e != cudaSuccess) return cuda_fail(e, "scattering_density launch");
-            if (launches) *launches += fast::launches_per_stage(FB_STAGE_SCATTERING_DENSITY);
+            if (launches) *launches += fast::launches_per_stage(c.P, FB_STAGE_SCATTERING_DENSITY, R);
             FB_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
             LaunchCtx cs = c;
             cs.stream = p->side;

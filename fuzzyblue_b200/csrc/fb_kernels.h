@@ -60,7 +60,7 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1);
 cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cudaEvent_t after_prep = nullptr);
 cudaError_t indirect_irradiance(const LaunchCtx& c, int order);
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1);
-int launches_per_stage(int stage);
+int launches_per_stage(const FbParams& P, int stage, int r_count);   // kernels one stage launches over r_count altitude levels
 }  // namespace fast
 
 // render_sky.frag and the library queries.

@@ -12,6 +12,9 @@
 #include "fb_kernels.h"
 
 #include <type_traits>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
 #include "fb_shader_math.cuh"
 
 namespace fb {
@@ -112,8 +115,8 @@ static inline DensityDims density_dims(const FbParams& P, int T) {
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
     return d;
 }
-// scratch: table [R][tiles][DL][T][ENT] floats (sized for the order-2 layout, the larger one) + ground normals
-// [R][DL] float4 + ground rows [R][DL/2][nE][3] float2: row 0 of delta_irradiance as (value, delta) pairs, multiplied
+// scratch: table [R][tiles][DL][T][ENT] floats (sized for the order-2 layout, the larger one) + ground-hit flags
+// [R][DL] + ground rows [R][DL/2][nE][3] float2: row 0 of delta_irradiance as (value, delta) pairs, multiplied
 // by the ground factor of (r, theta_l) for the eight downward theta rows (the others cannot reach the ground)
 static inline size_t density_tab_floats(const FbParams& P) {
     DensityDims d = density_dims(P, DensityCfg<true>::T);
@@ -123,13 +126,13 @@ static inline size_t density_grow_floats(const FbParams& P) { return (size_t)P.s
 
 size_t scratch_bytes(const FbParams& P) {
     if (!density_supported(P)) return 0;
-    return (density_tab_floats(P) + density_grow_floats(P)) * sizeof(float) + (size_t)P.scattering_r_size * DL * sizeof(float4);
+    return (density_tab_floats(P) + density_grow_floats(P) + (size_t)P.scattering_r_size * DL) * sizeof(float);
 }
 
 template <bool ORDER2>
 __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
                                                       Tex3 A0, Tex3 A1, DensityDims dd, float* __restrict__ tab,
-                                                      float4* __restrict__ gnd, const float4* __restrict__ dE_row0,
+                                                      float* __restrict__ hit, const float4* __restrict__ dE_row0,
                                                       float2* __restrict__ grow, int r0) {
     constexpr int ENT = DensityCfg<ORDER2>::ENT, TT = DensityCfg<ORDER2>::T;
     const int l = blockIdx.y, z = r0 + blockIdx.z;
@@ -145,27 +148,24 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
     const F ct = F(tg.ct16[l]), st = F(tg.st16[l]);
     const bool hits = a.RayIntersectsGround(r, ct);                                   // scattering_density.comp:45-46
     if (blockIdx.x == 0) {   // per-(r, theta) ground terms, scattering_density.comp:50-60, :81-87 (the whole block: r is uniform)
-        float gx = 0.f, gy = 0.f, gz = 0.f, nx = 0.f, nz = 0.f;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
         if (hits) {
             F dg = a.DistanceToBottom(r, ct);
             V tgr = a.Transmittance(T, r, ct, dg, true);
             V G = tgr * V(P.ground_albedo) * (F(1.f) / F(FB_PI_F));
-            // ground_normal = normalize(zenith*r + w_i*dg); its length does not depend on phi:
-            // (st*dg)^2 + (r + ct*dg)^2, so dot(normal, w_s) = q*(st*dg/len) + mu_s*((r + ct*dg)/len)
-            // with q = sx cos(phi) + sy sin(phi)
-            F vx = st * dg, vz = r + ct * dg;
-            F len = f_sqrt(vx * vx + vz * vz);
-            gx = G.x.v; gy = G.y.v; gz = G.z.v; nx = (vx / len).v; nz = (vz / len).v;
+            gx = G.x.v; gy = G.y.v; gz = G.z.v;
         }
-        if (threadIdx.x == 0) gnd[(size_t)z * DL + l] = make_float4(nx, nz, hits ? 1.f : 0.f, 0.f);
+        if (threadIdx.x == 0) hit[(size_t)z * DL + l] = hits ? 1.f : 0.f;   // the main kernel's ground-row mask
         if (l >= DL / 2) {   // GetIrradiance(bottom, .) only ever reads row 0 of delta_irradiance (irradiance.h:20-30)
             const int nE = P.irradiance_mu_s_size;
             float2* o = grow + ((size_t)z * (DL / 2) + (l - DL / 2)) * nE * 3;
             for (int i = threadIdx.x; i < nE; i += blockDim.x) {
                 const float4 v0 = __ldg(dE_row0 + i), v1 = __ldg(dE_row0 + min(i + 1, nE - 1));
-                o[i * 3] = make_float2(gx * v0.x, gx * (v1.x - v0.x));
-                o[i * 3 + 1] = make_float2(gy * v0.y, gy * (v1.y - v0.y));
-                o[i * 3 + 2] = make_float2(gz * v0.z, gz * (v1.z - v0.z));
+                // (intercept, slope) of the segment [i, i + 1): value(te) = intercept + te * slope, no fractional part needed
+                const float dx_ = gx * (v1.x - v0.x), dy_ = gy * (v1.y - v0.y), dz_ = gz * (v1.z - v0.z), fi = (float)i;
+                o[i * 3] = make_float2(fmaf(-fi, dx_, gx * v0.x), dx_);
+                o[i * 3 + 1] = make_float2(fmaf(-fi, dy_, gy * v0.y), dy_);
+                o[i * 3 + 2] = make_float2(fmaf(-fi, dz_, gz * v0.z), dz_);
             }
         }
     }
@@ -180,18 +180,24 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
     float* o = tab + ((((size_t)z * dd.tiles + tile) * DL + l) * TT + (size_t)msl * dd.nu + k) * ENT;
     const V4<F> s0 = sample<F>(A0, ux0, uvwz[2], uvwz[3]);
     const V4<F> s1 = last ? s0 : sample<F>(A0, ux1, uvwz[2], uvwz[3]);
+    // Entries are (intercept, slope) of the segment [k, k + 1) of the nu axis: value(tcx) = intercept + tcx * slope with
+    // tcx = u_nu * (nu - 1) the un-floored coordinate, so the consumer needs floor(tcx) for the address only.
+    const float fk = (float)k;
+    auto seg = [fk](F v0, F v1) { const float d = v1.v - v0.v; return make_float2(fmaf(-fk, d, v0.v), d); };
     if (ORDER2) {
         const V4<F> m0 = sample<F>(A1, ux0, uvwz[2], uvwz[3]);
         const V4<F> m1 = last ? m0 : sample<F>(A1, ux1, uvwz[2], uvwz[3]);
+        const float2 rx = seg(s0.x, s1.x), ry = seg(s0.y, s1.y), rz = seg(s0.z, s1.z);
+        const float2 mx = seg(m0.x, m1.x), my = seg(m0.y, m1.y), mz = seg(m0.z, m1.z);
         float4* o4 = reinterpret_cast<float4*>(o);
-        o4[0] = make_float4(s0.x.v, s1.x.v - s0.x.v, s0.y.v, s1.y.v - s0.y.v);
-        o4[1] = make_float4(s0.z.v, s1.z.v - s0.z.v, m0.x.v, m1.x.v - m0.x.v);
-        o4[2] = make_float4(m0.y.v, m1.y.v - m0.y.v, m0.z.v, m1.z.v - m0.z.v);
+        o4[0] = make_float4(rx.x, rx.y, ry.x, ry.y);
+        o4[1] = make_float4(rz.x, rz.y, mx.x, mx.y);
+        o4[2] = make_float4(my.x, my.y, mz.x, mz.y);
     } else {
         float2* o2 = reinterpret_cast<float2*>(o);
-        o2[0] = make_float2(s0.x.v, s1.x.v - s0.x.v);
-        o2[1] = make_float2(s0.y.v, s1.y.v - s0.y.v);
-        o2[2] = make_float2(s0.z.v, s1.z.v - s0.z.v);
+        o2[0] = seg(s0.x, s1.x);
+        o2[1] = seg(s0.y, s1.y);
+        o2[2] = seg(s0.z, s1.z);
     }
 }
 
@@ -216,22 +222,28 @@ __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; caller
     return y;
 }
 
+// Ground normals of the downward theta rows, (n_x, n_z) * scale per (r, l): CTA-uniform values the ground term needs
+// per sample.  As a kernel parameter they live in the constant bank and reach the FFMAs through uniform registers
+// (ULDC) instead of costing shared-memory wavefronts — the unit that binds this kernel.  One launch covers at most
+// GN_MAXR altitude levels.  They feed a look-up coordinate only, so the host evaluates them in double precision.
+constexpr int GN_MAXR = 64;
+struct GroundNormals { float2 n[GN_MAXR][DL / 2]; };
+
 template <bool ORDER2>
 __global__ void __launch_bounds__(256, 2)
 k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float* __restrict__ tabG,
-               const float4* __restrict__ gndG, const float2* __restrict__ growG, uint2* __restrict__ out, int r0,
-               uint32_t magic_tab, uint32_t magic_row) {
+               const float* __restrict__ hitG, const float2* __restrict__ growG, uint2* __restrict__ out, int r0,
+               uint32_t magic_tab, uint32_t magic_row, const __grid_constant__ GroundNormals GN) {
     typedef DensityCfg<ORDER2> C;
     constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
     constexpr int ENT_B = ENT * 4;                       // bytes per table entry
     constexpr int L_STRIDE = TT * ENT_B;                 // bytes per theta row block
     constexpr int TAB_B = DL * L_STRIDE;                 // 96 KiB
-    // shared memory map (bytes): [table TAB_B][geo TT*16][ground normals DL*8][2 mbarriers, padded to 128]
+    // shared memory map (bytes): [table TAB_B][geo TT*16][2 mbarriers, padded to 128]
     //                            [Wt DL*32*16 during the prologue, then the 8 ground rows (DL/2)*nE*24]
-    constexpr int GEO_OFF = TAB_B, NXZ_OFF = GEO_OFF + TT * 16, BAR_OFF = NXZ_OFF + DL * 8, GR_OFF = BAR_OFF + 128;
+    constexpr int GEO_OFF = TAB_B, BAR_OFF = GEO_OFF + TT * 16, GR_OFF = BAR_OFF + 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* geoS = reinterpret_cast<float4*>(smem_raw + GEO_OFF);
-    float2* nxzS = reinterpret_cast<float2*>(smem_raw + NXZ_OFF);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + BAR_OFF);
     float4* WtS = reinterpret_cast<float4*>(smem_raw + GR_OFF);
     const int nE = P.irradiance_mu_s_size;
@@ -288,11 +300,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         }
     }
     uint32_t gmask = 0;                                                        // theta rows that reach the ground (CTA-uniform)
-    for (int l = DL / 2; l < DL; ++l) {
-        const float4 g = __ldg(gndG + (size_t)z * DL + l);
-        if (g.z != 0.f) gmask |= 1u << l;
-        if (tid == l) nxzS[l] = make_float2(g.x, g.y);
-    }
+    for (int l = DL / 2; l < DL; ++l)
+        if (__ldg(hitG + (size_t)z * DL + l) != 0.f) gmask |= 1u << l;
     __syncthreads();
 
     // ---- per-lane constants: the weights of phi sample `lane` for the 16 theta rows (registers) ------------
@@ -354,14 +363,16 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             const float sc = n2 > 0.999998f ? 0.999999f * rsqrt_fast(n2) : 1.f;
             q *= sc; mus *= sc;
         }
+        if (!ORDER2) { q *= hn; mus *= hn; }                                      // tcx = hn * nu1 + hn in two FFMAs
         const uint32_t row_t = tab_base + (uint32_t)__float_as_int(geo.w);
         float ar = 0.f, ag = 0.f, ab = 0.f;
 #define FB_DENSITY_STEP(l)                                                                                              \
         {                                                                                                               \
-            const float nu1 = fmaf(mus, CT16[l], q * ST16[l]);                                                          \
-            const float tcx = fmaf(nu1, hn, hn);                                  /* scattering.h:146, in [0, nu-1) */  \
-            const float tm = __fadd_rd(tcx, MAGIC);                                                                     \
-            const float f = tcx - (tm - MAGIC);                                   /* scattering.h:148 */                \
+            float nu1, tcx;                                                       /* scattering.h:146, in [0, nu-1) */  \
+            if (ORDER2) { nu1 = fmaf(mus, CT16[l], q * ST16[l]); tcx = fmaf(nu1, hn, hn); }                             \
+            else { nu1 = 0.f; tcx = fmaf(mus, CT16[l], fmaf(q, ST16[l], hn)); }                                         \
+            const float tm = __fadd_rd(tcx, MAGIC);                               /* floor(tcx) in the low mantissa */  \
+            const float f = tcx;                                                  /* entries are (intercept, slope) */  \
             const uint32_t addr = row_t + __float_as_uint(tm) * (uint32_t)ENT_B;                                        \
             float Lr, Lg, Lb;                                                                                           \
             if (ORDER2) {                                                                                               \
@@ -379,11 +390,11 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                 Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);                           \
             }                                                                                                           \
             if (L0 >= 0 ? (l) >= L0 : ((l) >= DL / 2 && (gmask & (1u << (l))) != 0)) {  /* CTA-uniform */              \
-                const float2 N = lds64<NXZ_OFF + (l) * 8>(sbase);                 /* ground normal: (n_x, n_z) */       \
-                const float musg = fmaf(q, N.x, mus * N.y);                       /* dot(ground_normal, omega_s) */     \
-                const float te = fmaf(musg, e_c, e_c);                            /* irradiance.h:20-30, r = bottom */  \
+                const float2 N = GN.n[blockIdx.z][(l) - DL / 2];                  /* ground normal, uniform regs */     \
+                /* (dot(ground_normal, omega_s) + 1) * e_c, irradiance.h:20-30 at r = bottom; N is pre-scaled */        \
+                const float te = fmaf(q, N.x, fmaf(mus, N.y, e_c));                                                     \
                 const float em = __fadd_rd(te, MAGIC);                                                                  \
-                const float fe = te - (em - MAGIC);                                                                     \
+                const float fe = te;                                                                                    \
                 const uint32_t ea = erow_t + (uint32_t)((l) - DL / 2) * grow_b + __float_as_uint(em) * 24u;             \
                 const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);           \
                 Lr += fmaf(fe, er.y, er.x);                                       /* rows carry the ground factor */    \
@@ -417,7 +428,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
 template <bool ORDER2> static size_t density_smem(const FbParams& P) {
     typedef DensityCfg<ORDER2> C;
     const size_t wt = (size_t)DL * 32 * 16, gr = (size_t)(DL / 2) * P.irradiance_mu_s_size * 24;
-    return (size_t)DL * C::T * C::ENT * 4 + C::T * 16 + DL * 8 + 128 + (wt > gr ? wt : gr);
+    return (size_t)DL * C::T * C::ENT * 4 + C::T * 16 + 128 + (wt > gr ? wt : gr);
 }
 
 template <bool ORDER2>
@@ -428,21 +439,40 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     const size_t smem = density_smem<ORDER2>(P);
     float* tab = c.img.scratch;
     float2* grow = reinterpret_cast<float2*>(tab + density_tab_floats(P));
-    float4* gnd = reinterpret_cast<float4*>(tab + density_tab_floats(P) + density_grow_floats(P));
+    float* hit = tab + density_tab_floats(P) + density_grow_floats(P);
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     dim3 gp((W + 255) / 256, DL, r1 - r0);
-    dim3 gm(d.tiles, P.scattering_mu_size, r1 - r0);
-    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, gnd, c.img.delta_irradiance, grow, r0);
+    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, hit, c.img.delta_irradiance, grow, r0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // from here on nothing reads delta_irradiance: indirect_irradiance may run concurrently with the main kernel
     if (after_prep && (e = cudaEventRecord(after_prep, c.stream)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, gnd, grow,
-                                                                  c.img.scattering_density, r0,
-                                                                  0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u);
-    return cudaGetLastError();
+    // ground normals (scattering_density.comp:81-87) per (r, downward theta row); the look-up coordinate the kernel forms
+    // is te = (q n_x + mu_s n_z + 1) e_c with e_c = (nE - 1) / 2, and at order >= 3 its q, mu_s carry hn = (nu - 1) / 2
+    const double bot = P.bottom_radius, top = P.top_radius, Hh = std::sqrt(top * top - bot * bot);
+    const double e_c = 0.5 * (P.irradiance_mu_s_size - 1), ksc = ORDER2 ? e_c : e_c / (0.5 * (d.nu - 1));
+    for (int zc = r0; zc < r1; zc += GN_MAXR) {
+        const int nz_ = std::min(GN_MAXR, r1 - zc);
+        GroundNormals gn;
+        std::memset(&gn, 0, sizeof gn);
+        for (int i = 0; i < nz_; ++i) {
+            const double rho = P.scattering_r_size > 1 ? Hh * (zc + i) / (P.scattering_r_size - 1) : 0.0;   // scattering.h:64-67
+            const double r = std::sqrt(rho * rho + bot * bot);
+            for (int l = DL / 2; l < DL; ++l) {
+                const double ct = c.trig.ct16[l], st = c.trig.st16[l];
+                const double dg = std::max(-r * ct - std::sqrt(std::max(r * r * (ct * ct - 1.0) + bot * bot, 0.0)), 0.0);
+                const double vx = st * dg, vz = r + ct * dg, len = std::sqrt(vx * vx + vz * vz);
+                gn.n[i][l - DL / 2] = make_float2((float)(vx / len * ksc), (float)(vz / len * ksc));
+            }
+        }
+        dim3 gm(d.tiles, P.scattering_mu_size, nz_);
+        k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, hit, grow, c.img.scattering_density, zc,
+                                                                      0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u, gn);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cudaEvent_t after_prep) {
@@ -844,7 +874,10 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     return multiple_launch<8, 1024>(c, nt, CH, smem, r0, r1);
 }
 
-int launches_per_stage(int stage) { return stage == FB_STAGE_SCATTERING_DENSITY ? 2 : 1; }
+int launches_per_stage(const FbParams& P, int stage, int r_count) {
+    if (stage != FB_STAGE_SCATTERING_DENSITY || !density_supported(P)) return 1;
+    return 1 + (r_count + GN_MAXR - 1) / GN_MAXR;   // preparation + one main launch per GN_MAXR levels
+}
 
 }  // namespace fast
 }  // namespace fb

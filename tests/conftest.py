@@ -30,6 +30,17 @@ DUMP_DIMS = dict(scattering_r_size=16, scattering_mu_size=64, scattering_mu_s_si
 WIDE_DIMS = dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=64, scattering_nu_size=32, order=3)
 
 
+# more altitude levels than one density launch carries ground normals for (64), and an irradiance table that is not 64 wide
+TALL_DIMS = dict(scattering_r_size=72, scattering_mu_size=4, scattering_mu_s_size=4, scattering_nu_size=2,
+                 irradiance_mu_s_size=40, irradiance_r_size=8, order=3)
+
+
+@pytest.fixture(scope="session")
+def oracle_tall_f32():
+    from oracle import oracle as O
+    return O.precompute(O.Params(**TALL_DIMS), O.F32, keep_history=True)
+
+
 @pytest.fixture(scope="session")
 def oracle_wide_f32():
     from oracle import oracle as O

@@ -15,7 +15,7 @@ import fuzzyblue_b200 as fb
 from fuzzyblue_b200 import api
 from oracle import oracle as O
 
-from .conftest import DUMP_DIMS, SMOKE_DIMS, WIDE_DIMS
+from .conftest import DUMP_DIMS, SMOKE_DIMS, WIDE_DIMS, TALL_DIMS
 
 pytestmark = pytest.mark.gpu
 
@@ -195,6 +195,22 @@ def test_wide_rows(builder, oracle_wide_f32):
         check(f"wide delta_multiple_scattering(order {o})",
               err16(pend.download(api.IMAGE_DELTA_MULTIPLE_SCATTERING), ref.history[o]["delta_multiple_scattering"]))
         check(f"wide scattering(order {o})", err16(pend.download(api.IMAGE_SCATTERING), ref.history[o]["scattering"]))
+
+
+def test_tall_table(builder, oracle_tall_f32):
+    """72 altitude levels (the density kernel carries the ground normals of 64 levels per launch) and a 40-wide
+    irradiance table (ground rows of another size than the default): density at both orders against the oracle on
+    identical inputs, then the whole precompute."""
+    ref = oracle_tall_f32
+    dims = dict(TALL_DIMS)
+    order = dims.pop("order")
+    for o in (2, 3):
+        pend = staged(builder, dims, inputs_of_order(ref, o), order=order)
+        pend.run_stage(api.STAGE_SCATTERING_DENSITY, order=o)
+        check(f"tall scattering_density(order {o})", err16(pend.download(api.IMAGE_SCATTERING_DENSITY), ref.history[o]["scattering_density"]))
+    T, S, E = fb.precompute_host(builder, fb.Parameters(order=order, **dims))
+    check_compounded("tall scattering", err16(S, ref.scattering))
+    check_compounded("tall irradiance", err32(E, ref.irradiance))
 
 
 @pytest.mark.parametrize("index", [0, 1, 2])
