@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfuzzyblue_b200.so")
+LIB_PATH = os.environ.get("FUZZYBLUE_B200_LIB") or os.path.join(_HERE, "csrc", "libfuzzyblue_b200.so")   # override: kernel experiments
 
 # enums of include/fuzzyblue.h
 FB_OK = 0

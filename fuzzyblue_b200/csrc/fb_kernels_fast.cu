@@ -96,13 +96,20 @@ __device__ constexpr float ST16[DL] = {0.0980171412f, 0.290284663f, 0.471396744f
 // kernel and an LDS costs one wavefront per 4 bytes per lane whatever the address pattern (tools/lds_bench.cu).
 //   order >= 3 entry, 24 B:  [R.r dR.r | R.g dR.g | R.b dR.b]                              3 x LDS.64
 //   order 2    entry, 48 B:  [R.r dR.r R.g dR.g | R.b dR.b M.r dM.r | M.g dM.g M.b dM.b]   3 x LDS.128
+#ifndef FB_PAIR_O2
+#define FB_PAIR_O2 0
+#endif
+#ifndef FB_PAIR_O3
+#define FB_PAIR_O3 1
+#endif
 template <bool ORDER2> struct DensityCfg {
+    static constexpr bool PAIRED = ORDER2 ? FB_PAIR_O2 != 0 : FB_PAIR_O3 != 0;   // mirror-sample body for coplanar texels
     static constexpr int ENT = ORDER2 ? 12 : 6;       // floats per table entry
     static constexpr int T = ORDER2 ? 128 : 256;      // texels per CTA = ms_tile * nu
     static constexpr int NWARPS = 8;
 };
 struct DensityDims {
-    int nu, ms_tile, tiles;
+    int nu, ms_tile, tiles, ms_shift;   // ms_tile = 1 << ms_shift (nu and the CTA's texel count are powers of two)
 };
 static inline bool density_supported(const FbParams& P) {
     const int nu = P.scattering_nu_size;
@@ -112,6 +119,8 @@ static inline DensityDims density_dims(const FbParams& P, int T) {
     DensityDims d;
     d.nu = P.scattering_nu_size;
     d.ms_tile = T / d.nu;
+    d.ms_shift = 0;
+    while ((1 << d.ms_shift) < d.ms_tile) ++d.ms_shift;
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
     return d;
 }
@@ -222,6 +231,29 @@ __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; caller
     return y;
 }
 
+// One sample of the integrand for the paired body's slow branch (a table knot between two mirror samples): the look-up
+// of FB_DENSITY_STEP as a function.  TOFF / GOFF are the immediate offsets of the theta row and of the ground rows.
+template <bool ORDER2, int TOFF, int GOFF>
+__device__ __forceinline__ void density_tap(uint32_t addr, float f, float nu1, float kR, float kMR, float g2p1, float m2g, bool gnd,
+                                            uint32_t ea, float te, float& Lr, float& Lg, float& Lb) {
+    if (ORDER2) {
+        const float4 t0 = lds128<TOFF>(addr), t1 = lds128<TOFF + 16>(addr), t2 = lds128<TOFF + 32>(addr);
+        const float pr = fmaf(nu1 * kR, nu1, kR);
+        const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));
+        const float pm = pr * kMR * (rs * rs * rs);
+        Lr = fmaf(fmaf(f, t1.w, t1.z), pm, fmaf(f, t0.y, t0.x) * pr);
+        Lg = fmaf(fmaf(f, t2.y, t2.x), pm, fmaf(f, t0.w, t0.z) * pr);
+        Lb = fmaf(fmaf(f, t2.w, t2.z), pm, fmaf(f, t1.y, t1.x) * pr);
+    } else {
+        const float2 cr = lds64<TOFF>(addr), cg = lds64<TOFF + 8>(addr), cb = lds64<TOFF + 16>(addr);
+        Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);
+    }
+    if (gnd) {
+        const float2 er = lds64<GOFF>(ea), eg = lds64<GOFF + 8>(ea), eb = lds64<GOFF + 16>(ea);
+        Lr += fmaf(te, er.y, er.x); Lg += fmaf(te, eg.y, eg.x); Lb += fmaf(te, eb.y, eb.x);
+    }
+}
+
 // Ground normals of the downward theta rows, (n_x, n_z) * scale per (r, l): CTA-uniform values the ground term needs
 // per sample.  As a kernel parameter they live in the constant bank and reach the FFMAs through uniform registers
 // (ULDC) instead of costing shared-memory wavefronts — the unit that binds this kernel.  One launch covers at most
@@ -236,16 +268,19 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                uint32_t magic_tab, uint32_t magic_row, const __grid_constant__ GroundNormals GN) {
     typedef DensityCfg<ORDER2> C;
     constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
+    constexpr bool PAIRED = C::PAIRED;
     constexpr int ENT_B = ENT * 4;                       // bytes per table entry
     constexpr int L_STRIDE = TT * ENT_B;                 // bytes per theta row block
     constexpr int TAB_B = DL * L_STRIDE;                 // 96 KiB
-    // shared memory map (bytes): [table TAB_B][geo TT*16][2 mbarriers, padded to 128]
+    // shared memory map (bytes): [table TAB_B][geo TT*16][2 mbarriers, per-warp leader counts and follower masks: 128]
     //                            [Wt DL*32*16 during the prologue, then the 8 ground rows (DL/2)*nE*24]
     constexpr int GEO_OFF = TAB_B, BAR_OFF = GEO_OFF + TT * 16, GR_OFF = BAR_OFF + 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* geoS = reinterpret_cast<float4*>(smem_raw + GEO_OFF);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + BAR_OFF);
     float4* WtS = reinterpret_cast<float4*>(smem_raw + GR_OFF);
+    int* cntS = reinterpret_cast<int*>(smem_raw + BAR_OFF + 16);           // per warp: general | paired << 16 leaders
+    uint32_t* folS = reinterpret_cast<uint32_t*>(smem_raw + BAR_OFF + 64);  // per warp: follower mask of its 32 texels
     const int nE = P.irradiance_mu_s_size;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,6 +346,53 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         const float4 w = WtS[l * 32 + lane];
         Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
     }
+    // ---- work list ------------------------------------------------------------------------------------------
+    // Every nu knot outside [mu mu_s - s, mu mu_s + s] is clamped onto the same bound (scattering.h:133-136), so a
+    // texel whose (sx, sy, mu_s) equal those of the previous nu slice has bit-identical inputs: it is a FOLLOWER and
+    // receives its leader's result (5.5 % of the texels at default dims).  A leader whose sun direction lies in the
+    // (zenith, view) plane -- sy ~ 0: every clamped texel, 25 % of the table -- takes the paired body below.
+    const float hn = 0.5f * (float)(dd.nu - 1);
+    static_assert(TT <= NWARPS * 32 && TT * ENT_B <= (1 << 14), "one thread classifies one texel; packed record fields");
+    int nGen = 0, nPair = 0;
+    {
+        bool isGen = false, isPair = false, follower = false;
+        const int t = tid;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < TT) {
+            g = geoS[t];
+            if (__float_as_int(g.w) >= 0) {
+                if (t >= dd.ms_tile) {
+                    const float4* pg = geoS + (t - dd.ms_tile);
+                    follower = __float_as_int(pg->x) == __float_as_int(g.x) && __float_as_int(pg->y) == __float_as_int(g.y) &&
+                               __float_as_int(pg->z) == __float_as_int(g.z);
+                }
+                if (follower) {}
+                else if (PAIRED && g.y * hn <= 0.00390625f) isPair = true;
+                else isGen = true;
+            }
+        }
+        // ordered compaction (ballot + per-warp counts): the records are sorted by texel, so the half-warp a paired texel
+        // lands in -- and with it the last-ulp rounding of its mirror trig values -- is the same on every run
+        const uint32_t bg = __ballot_sync(0xffffffffu, isGen), bp = __ballot_sync(0xffffffffu, isPair);
+        const uint32_t bf = __ballot_sync(0xffffffffu, follower);
+        if (lane == 0) { cntS[warp] = __popc(bg) | (__popc(bp) << 16); folS[warp] = bf; }
+        __syncthreads();                      // counts and follower masks visible; nobody reads the un-compacted records any more
+        int before = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            const int c = cntS[w];
+            if (w < warp) before += c;
+            nGen += c & 0xffff; nPair += c >> 16;
+        }
+        if (isGen || isPair) {
+            int nf = 0;                       // followers: the run of flagged texels in the next nu slices
+            for (int u = t + dd.ms_tile; u < TT && ((folS[u >> 5] >> (u & 31)) & 1u); u += dd.ms_tile) ++nf;
+            // record .w: byte offset of the texel's table rows | texel << 14 | followers << 22
+            g.w = __int_as_float(__float_as_int(g.w) | (t << 14) | (nf << 22));
+            const uint32_t lt = (1u << lane) - 1u;
+            geoS[isGen ? (before & 0xffff) + __popc(bg & lt) : TT - 1 - ((before >> 16) + __popc(bp & lt))] = g;
+        }
+    }
     __syncthreads();                          // every warp holds its weights: their region now receives the ground rows
     const uint32_t grow_b = (uint32_t)nE * 24u;                                // bytes per ground row
     if (gmask && tid == 0) {
@@ -319,7 +401,6 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         tma_bulk_g2s(smem_raw + GR_OFF, growG + (size_t)z * (DL / 2) * nE * 3, (DL / 2) * grow_b, bar + 1);
     }
     const float cp = tg.cp32[lane], sp = tg.sp32[lane];
-    const float hn = 0.5f * (float)(dd.nu - 1);
     const float MAGIC = 8388608.f;   // 2^23: x + MAGIC rounded down leaves floor(x) in the low mantissa bits
     // GetIrradiance at r = bottom lands on row 0: u*N - 0.5 = (mu_s*0.5 + 0.5)*(N - 1)
     const float e_c = 0.5f * (float)(nE - 1);
@@ -348,12 +429,18 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     // one does).  The two patterns an Earth-like shell produces are compiled with L0 fixed: the 16 unrolled steps then
     // form one basic block and the loads of later steps are scheduled across the ground terms of earlier ones.  Any
     // other pattern takes the L0 = -1 body, which tests the mask per step.
+    auto store = [&](int rec, float ar, float ag, float ab) {                 // the texel and its followers
+        const uint2 v = pack_half4(ar, ag, ab, 0.f);
+        const int t = (rec >> 14) & 0xff;
+        uint2* o = out + (out_row + (t >> dd.ms_shift) * P.scattering_mu_s_size + tile * dd.ms_tile + (t & (dd.ms_tile - 1)));
+#pragma unroll 1
+        for (int nf = rec >> 22; nf >= 0; --nf, o += P.scattering_mu_s_size) *o = v;   // followers: the next nu slices
+    };
     auto texels = [&](auto L0c) __attribute__((always_inline)) {
     constexpr int L0 = decltype(L0c)::value;
 #pragma unroll 2
-    for (int t = warp; t < TT; t += NWARPS) {
-        const float4 geo = geoS[t];
-        if (__float_as_int(geo.w) < 0) continue;                                  // padding texel of a partial tile
+    for (int i = warp; i < nGen; i += NWARPS) {
+        const float4 geo = geoS[i];
         // w_s . w_i = sin(theta_l) * q + mu_s * cos(theta_l) with q = sx cos(phi) + sy sin(phi) per (texel, lane).
         // |w_s . w_i| <= sqrt(q^2 + mu_s^2) for every theta; pull (q, mu_s) inside the unit disc by a hair so that
         // neither the nu look-up below nor the ground look-up can step outside its table row — no per-sample clamps.
@@ -364,7 +451,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             q *= sc; mus *= sc;
         }
         if (!ORDER2) { q *= hn; mus *= hn; }                                      // tcx = hn * nu1 + hn in two FFMAs
-        const uint32_t row_t = tab_base + (uint32_t)__float_as_int(geo.w);
+        const uint32_t row_t = tab_base + ((uint32_t)__float_as_int(geo.w) & 0x3fffu);
         float ar = 0.f, ag = 0.f, ab = 0.f;
 #define FB_DENSITY_STEP(l)                                                                                              \
         {                                                                                                               \
@@ -414,10 +501,142 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             ag += __shfl_xor_sync(0xffffffffu, ag, s);
             ab += __shfl_xor_sync(0xffffffffu, ab, s);
         }
-        if (lane == 0) {
-            const int nui = t / dd.ms_tile, ms = tile * dd.ms_tile + t % dd.ms_tile;
-            out[out_row + nui * P.scattering_mu_s_size + ms] = pack_half4(ar, ag, ab, 0.f);
+        if (lane == 0) store(__float_as_int(geo.w), ar, ag, ab);
+    }
+    // ---- paired body: two texels per warp (lanes 0-15 / 16-31), a lane takes the mirror samples phi_m and 2 pi - phi_m
+    // (same cos phi, hence the same phase weight; sin phi flips).  With sy ~ 0 both fall into the same table segment
+    // [k, k + 1) except when a knot lies between them, and on a segment L(a) + L(b) = 2 (intercept + slope * mean):
+    // one table entry serves two samples.  The warp checks `same segment` per step and otherwise gives each sample its
+    // own entry, so the result is the general body's up to summation order.
+    if (PAIRED)
+    for (int i = warp; 2 * i < nPair; i += NWARPS) {
+        const int idx = 2 * i + (lane >> 4);
+        const bool valid = idx < nPair;                                          // odd count: the last half-warp idles
+        const float4 geo = geoS[TT - 1 - (valid ? idx : idx - 1)];
+        const float qm0 = geo.x * cp, qd0 = geo.y * sp;
+        float mus = geo.z;
+        const float qx = fmaxf(fabsf(qm0 + qd0), fabsf(qm0 - qd0));
+        const float n2 = fmaf(qx, qx, mus * mus);
+        float sc = n2 > 0.999998f ? 0.999999f * rsqrt_fast(n2) : 1.f;            // one pull for both samples of the pair
+        if (!ORDER2) sc *= hn;
+        const float qm = qm0 * sc, qd = qd0 * sc, qdn = -qd;
+        mus *= sc;
+        const uint32_t row_t = tab_base + ((uint32_t)__float_as_int(geo.w) & 0x3fffu);
+        float ar = 0.f, ag = 0.f, ab = 0.f;
+        uint32_t straddle = 0;                                                   // bit l: table knot, bit 16 + l: ground-row knot
+#define FB_PAIR_STEP(l)                                                                                                 \
+        {                                                                                                               \
+            const bool gnd = L0 >= 0 ? (l) >= L0 : ((l) >= DL / 2 && (gmask & (1u << (l))) != 0);   /* CTA-uniform */   \
+            float nu1a = 0.f, nu1b = 0.f, fa, fb, fm = 0.f;                                                             \
+            if (ORDER2) {                                                                                               \
+                const float nm = fmaf(mus, CT16[l], qm * ST16[l]);                                                      \
+                nu1a = fmaf(qd, ST16[l], nm); nu1b = fmaf(qdn, ST16[l], nm);                                            \
+                fa = fmaf(nu1a, hn, hn); fb = fmaf(nu1b, hn, hn);                                                       \
+            } else {                                                                                                    \
+                fm = fmaf(mus, CT16[l], fmaf(qm, ST16[l], hn));                                                         \
+                fa = fmaf(qd, ST16[l], fm); fb = fmaf(qdn, ST16[l], fm);                                                \
+            }                                                                                                           \
+            const float ta = __fadd_rd(fa, MAGIC), tb = __fadd_rd(fb, MAGIC);                                           \
+            if (ta != tb) straddle |= 1u << (l);                                  /* a nu knot between the two */       \
+            const uint32_t addr = row_t + __float_as_uint(ta) * (uint32_t)ENT_B;                                        \
+            float Lr, Lg, Lb;                                                                                           \
+            if (ORDER2) {                                                                                               \
+                const float4 t0 = lds128<(l) * L_STRIDE>(addr), t1 = lds128<(l) * L_STRIDE + 16>(addr),                 \
+                             t2 = lds128<(l) * L_STRIDE + 32>(addr);                                                    \
+                const float pra = fmaf(nu1a * kR, nu1a, kR), prb = fmaf(nu1b * kR, nu1b, kR);                           \
+                const float rsa = rsqrt_fast(fmaf(m2g, nu1a, g2p1)), rsb = rsqrt_fast(fmaf(m2g, nu1b, g2p1));           \
+                const float pma = pra * kMR * (rsa * rsa * rsa), pmb = prb * kMR * (rsb * rsb * rsb);                   \
+                Lr = fmaf(fmaf(fa, t1.w, t1.z), pma, fmaf(fa, t0.y, t0.x) * pra) +                                      \
+                     fmaf(fmaf(fb, t1.w, t1.z), pmb, fmaf(fb, t0.y, t0.x) * prb);                                       \
+                Lg = fmaf(fmaf(fa, t2.y, t2.x), pma, fmaf(fa, t0.w, t0.z) * pra) +                                      \
+                     fmaf(fmaf(fb, t2.y, t2.x), pmb, fmaf(fb, t0.w, t0.z) * prb);                                       \
+                Lb = fmaf(fmaf(fa, t2.w, t2.z), pma, fmaf(fa, t1.y, t1.x) * pra) +                                      \
+                     fmaf(fmaf(fb, t2.w, t2.z), pmb, fmaf(fb, t1.y, t1.x) * prb);                                       \
+            } else {                          /* half sums: the texel's total is doubled after the loop */              \
+                const float2 cr = lds64<(l) * L_STRIDE>(addr), cg = lds64<(l) * L_STRIDE + 8>(addr),                    \
+                             cb = lds64<(l) * L_STRIDE + 16>(addr);                                                     \
+                Lr = fmaf(fm, cr.y, cr.x); Lg = fmaf(fm, cg.y, cg.x); Lb = fmaf(fm, cb.y, cb.x);                        \
+            }                                                                                                           \
+            if (gnd) {                                                                                                  \
+                const float2 N = GN.n[blockIdx.z][(l) >= DL / 2 ? (l) - DL / 2 : 0];                                    \
+                const float tem = fmaf(qm, N.x, fmaf(mus, N.y, e_c));                                                   \
+                const float ema = __fadd_rd(fmaf(qd, N.x, tem), MAGIC), emb = __fadd_rd(fmaf(qdn, N.x, tem), MAGIC);    \
+                if (ema != emb) straddle |= 0x10000u << (l);                      /* an irradiance knot between them */ \
+                const uint32_t ea = erow_t + (uint32_t)((l) - DL / 2) * grow_b + __float_as_uint(ema) * 24u;            \
+                const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);           \
+                if (ORDER2) {                                                                                           \
+                    Lr = fmaf(2.f, fmaf(tem, er.y, er.x), Lr);                                                          \
+                    Lg = fmaf(2.f, fmaf(tem, eg.y, eg.x), Lg);                                                          \
+                    Lb = fmaf(2.f, fmaf(tem, eb.y, eb.x), Lb);                                                          \
+                } else {                                                                                                \
+                    Lr += fmaf(tem, er.y, er.x); Lg += fmaf(tem, eg.y, eg.x); Lb += fmaf(tem, eb.y, eb.x);              \
+                }                                                                                                       \
+            }                                                                                                           \
+            ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);                               \
         }
+        FB_PAIR_STEP(0) FB_PAIR_STEP(1) FB_PAIR_STEP(2) FB_PAIR_STEP(3)
+        FB_PAIR_STEP(4) FB_PAIR_STEP(5) FB_PAIR_STEP(6) FB_PAIR_STEP(7)
+        FB_PAIR_STEP(8) FB_PAIR_STEP(9) FB_PAIR_STEP(10) FB_PAIR_STEP(11)
+        FB_PAIR_STEP(12) FB_PAIR_STEP(13) FB_PAIR_STEP(14) FB_PAIR_STEP(15)
+#undef FB_PAIR_STEP
+        // The rare sample b that sits beyond a knot was evaluated on a's segment: add (its own segment - a's segment) at
+        // its coordinate.  A compact loop over the affected theta rows (run-time l: the weights come out of the register
+        // file through a select chain); per-lane predicates only, so a texel's result does not depend on its partner.
+        {
+            const uint32_t any = __reduce_or_sync(0xffffffffu, straddle);
+            uint32_t steps = (any | (any >> 16)) & 0xffffu;
+            while (steps) {
+                const int l = __ffs((int)steps) - 1;
+                steps &= steps - 1;
+                float wr = Wr[0], wg = Wg[0], wb = Wb[0];
+#pragma unroll
+                for (int j = 1; j < DL; ++j)
+                    if (l == j) { wr = Wr[j]; wg = Wg[j]; wb = Wb[j]; }
+                const float ct = CT16[l], st = ST16[l];
+                const float hs = ORDER2 ? 1.f : 0.5f;
+                float dr = 0.f, dg = 0.f, db = 0.f;
+                if (straddle & (1u << l)) {
+                    float nu1b = 0.f, fa, fb;
+                    if (ORDER2) {
+                        const float nm = fmaf(mus, ct, qm * st);
+                        nu1b = fmaf(qdn, st, nm);
+                        fa = fmaf(fmaf(qd, st, nm), hn, hn); fb = fmaf(nu1b, hn, hn);
+                    } else {
+                        const float fm = fmaf(mus, ct, fmaf(qm, st, hn));
+                        fa = fmaf(qd, st, fm); fb = fmaf(qdn, st, fm);
+                    }
+                    const uint32_t lrow = row_t + (uint32_t)(l * L_STRIDE);
+                    const uint32_t addra = lrow + __float_as_uint(__fadd_rd(fa, MAGIC)) * (uint32_t)ENT_B;
+                    const uint32_t addrb = lrow + __float_as_uint(__fadd_rd(fb, MAGIC)) * (uint32_t)ENT_B;
+                    float r1, g1, b1, r2, g2, b2;
+                    density_tap<ORDER2, 0, GR_OFF>(addrb, fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r1, g1, b1);
+                    density_tap<ORDER2, 0, GR_OFF>(addra, fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r2, g2, b2);
+                    dr = hs * (r1 - r2); dg = hs * (g1 - g2); db = hs * (b1 - b2);
+                }
+                if (straddle & (0x10000u << l)) {                                  // only ever set for l >= DL / 2
+                    const float2 N = GN.n[blockIdx.z][(l - DL / 2) & (DL / 2 - 1)];
+                    const float tem = fmaf(qm, N.x, fmaf(mus, N.y, e_c));
+                    const float teb = fmaf(qdn, N.x, tem);
+                    const uint32_t grow_l = erow_t + (uint32_t)(l - DL / 2) * grow_b;
+                    const uint32_t ea = grow_l + __float_as_uint(__fadd_rd(fmaf(qd, N.x, tem), MAGIC)) * 24u;
+                    const uint32_t eb_ = grow_l + __float_as_uint(__fadd_rd(teb, MAGIC)) * 24u;
+                    const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);
+                    const float2 fr = lds64<GR_OFF>(eb_), fg = lds64<GR_OFF + 8>(eb_), fbb = lds64<GR_OFF + 16>(eb_);
+                    dr += hs * (fmaf(teb, fr.y, fr.x) - fmaf(teb, er.y, er.x));
+                    dg += hs * (fmaf(teb, fg.y, fg.x) - fmaf(teb, eg.y, eg.x));
+                    db += hs * (fmaf(teb, fbb.y, fbb.x) - fmaf(teb, eb.y, eb.x));
+                }
+                ar = fmaf(dr, wr, ar); ag = fmaf(dg, wg, ag); ab = fmaf(db, wb, ab);
+            }
+        }
+        if (!ORDER2) { ar += ar; ag += ag; ab += ab; }
+#pragma unroll
+        for (int s = 8; s > 0; s >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, s);
+            ag += __shfl_xor_sync(0xffffffffu, ag, s);
+            ab += __shfl_xor_sync(0xffffffffu, ab, s);
+        }
+        if ((lane & 15) == 0 && valid) store(__float_as_int(geo.w), ar, ag, ab);
     }
     };
     if (gmask == 0xFF00u) texels(std::integral_constant<int, 8>());
