@@ -934,10 +934,20 @@ struct MultiNode {       // per trapezoid node, block-uniform; three 16-byte wor
 };
 
 
+#ifndef FB_MS_U
+#define FB_MS_U 4        // nodes whose density rows are in flight together during staging
+#endif
+#ifndef FB_MS_MINB
+#define FB_MS_MINB 4     // CTAs per SM of the 256-thread variant
+#endif
+#ifndef FB_MS_CU
+#define FB_MS_CU 4       // unroll of the per-texel node loop
+#endif
 template <int TPT, int NTMAX>   // TPT texels per thread: the CTA covers the whole (nu, mu_s) row, W <= TPT * blockDim.x
-__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
+__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : 1) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
                                                               uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CU = FB_MS_CU;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     MultiNode* nodes = reinterpret_cast<MultiNode*>(smem_raw);
     float4* slab = reinterpret_cast<float4*>(smem_raw + sizeof(MultiNode) * NS);
     const int NU = P.scattering_nu_size, MS = P.scattering_mu_s_size, W = NU * MS;
@@ -957,14 +967,44 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scatte
         const F tcx = (nu + F(1.f)) / F(2.f) * F((float)(NU - 1));
         const F txf = f_floor(tcx);
         ln[k] = (tcx - txf).v;
-        const int tx = min(max((int)txf.v, 0), NU - 1);
+        int tx = min(max((int)txf.v, 0), NU - 1);
+        // An un-clamped nu is a knot value, but (nu + 1) / 2 * (NU - 1) may round to k - 1 ulp: the as-written blend is then
+        // v[k - 1] * 6e-8 + v[k] * (1 - 6e-8).  Such a texel is put onto its knot (a 1e-7-relative change of a convex
+        // blend, the same class as FMA contraction), so that only clamped texels ever read two nu slices.
+        if (ln[k] > 0.999999f) { tx = min(tx + 1, NU - 1); ln[k] = 0.f; }
+        else if (ln[k] < 0.000001f) ln[k] = 0.f;
         kx0[k] = tx * MS; kx1[k] = min(tx + 1, NU - 1) * MS;
         rmus[k] = (r * mu_s).v; nuf[k] = nu.v;
         ar[k] = ag[k] = ab[k] = 0.f;
         // a texel whose nu was not clamped sits on a nu knot: lerp == 0 exactly and fma(0, v1 - v0, v0) == v0, so the
-        // second slice need not be fetched (bit-identical; 65 % of the texels at default dims, but every warp holds
-        // a clamped lane -- mu_s = 1 admits a single nu -- so this is predication, not a uniform branch)
+        // second slice need not be fetched (bit-identical; 65 % of the texels at default dims)
         two[k] = ln[k] != 0.f;
+    }
+    // Texels of one mu_s column whose nu knots were clamped onto the same bound (scattering.h:133-136) have bit-identical
+    // inputs.  A run of equal nu that contains slice 0 is led by slice 0, any other run by its top slice: at default dims
+    // the leaders of clamped runs then all sit in the first and the last warp, and the six warps in between hold only
+    // un-clamped texels (one slice, warp-uniformly) and followers, which wait for their leader's result.
+    int leader[TPT];
+    {
+        float* nuS = reinterpret_cast<float*>(slab);                     // aliases the slab: consumed before the first staging pass
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            const int x = threadIdx.x + k * blockDim.x;
+            if (x < W) nuS[x] = nuf[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            const int x = threadIdx.x + k * blockDim.x;
+            leader[k] = x;
+            if (x < W) {
+                const int me = __float_as_int(nuf[k]);
+                int lo = x, hi = x;
+                while (lo >= MS && __float_as_int(nuS[lo - MS]) == me) lo -= MS;
+                while (hi + MS < W && __float_as_int(nuS[hi + MS]) == me) hi += MS;
+                leader[k] = lo < MS ? lo : hi;
+            }
+        }
     }
     for (int i = threadIdx.x; i < NS; i += blockDim.x) {
         const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);                        // multiple_scattering.comp:23-26
@@ -1004,25 +1044,41 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scatte
             const int x = threadIdx.x + k * blockDim.x;
             if (x < W) {
                 const uint32_t xi = (uint32_t)x;
-#pragma unroll 3
-                for (int e = 0; e < cn; ++e) {    // stage: (mu, r)-bilinear of the density table at this x, per node
-                    const float4 w = nodes[c0 + e].w;
-                    const uint4 o = nodes[c0 + e].off;   // 32-bit texel indices: one IMAD.WIDE per address
-                    const float4 a00 = unpack_half4(__ldg(dens + (o.x + xi))), a10 = unpack_half4(__ldg(dens + (o.y + xi)));
-                    const float4 a01 = unpack_half4(__ldg(dens + (o.z + xi))), a11 = unpack_half4(__ldg(dens + (o.w + xi)));
-                    float4 v;
-                    v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
-                    v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
-                    v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
-                    v.w = 0.f;
-                    slab[e * W + x] = v;
+                // stage: (mu, r)-bilinear of the density table at this x, per node.  The four row loads of FB_MS_U nodes
+                // are issued before the first blend, so 4 * FB_MS_U loads are in flight per thread (one node at a time
+                // left the loop waiting on L2 latency every iteration).
+                for (int e0 = 0; e0 < cn; e0 += FB_MS_U) {
+                    uint2 raw[FB_MS_U][4];
+#pragma unroll
+                    for (int u = 0; u < FB_MS_U; ++u) {
+                        const uint4 o = nodes[c0 + min(e0 + u, cn - 1)].off;   // 32-bit texel indices: one IMAD.WIDE per address
+                        raw[u][0] = __ldg(dens + (o.x + xi)); raw[u][1] = __ldg(dens + (o.y + xi));
+                        raw[u][2] = __ldg(dens + (o.z + xi)); raw[u][3] = __ldg(dens + (o.w + xi));
+                    }
+#pragma unroll
+                    for (int u = 0; u < FB_MS_U; ++u) {
+                        if (e0 + u < cn) {
+                            const float4 w = nodes[c0 + e0 + u].w;
+                            const float4 a00 = unpack_half4(raw[u][0]), a10 = unpack_half4(raw[u][1]);
+                            const float4 a01 = unpack_half4(raw[u][2]), a11 = unpack_half4(raw[u][3]);
+                            float4 v;
+                            v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
+                            v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
+                            v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
+                            v.w = 0.f;
+                            slab[(e0 + u) * W + x] = v;
+                        }
+                    }
                 }
             }
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < TPT; ++k) {
-            if ((int)(threadIdx.x + k * blockDim.x) < W) {
+            const int xk = threadIdx.x + k * blockDim.x;
+            const bool act = xk < W && leader[k] == xk;
+            const bool any_two = __any_sync(0xffffffffu, act && two[k]);   // warp-uniform: does any lane need slice 2
+            if (act) {
 #define FB_MS_SAMPLE(TWO)                                                                                                   \
                 for (int e = 0; e < cn; ++e) {                                                                              \
                     const float4 nt = nodes[c0 + e].t;                                                                      \
@@ -1048,16 +1104,29 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? 4 : 1) k_multiple_scatte
                     ag[k] = fmaf(vg, nt.y, ag[k]);                                                                          \
                     ab[k] = fmaf(vb, nt.z, ab[k]);                                                                          \
                 }
-#pragma unroll 4
-                FB_MS_SAMPLE(two[k])
+                if (any_two) {
+#pragma unroll CU
+                    FB_MS_SAMPLE(two[k])
+                } else {
+#pragma unroll CU
+                    FB_MS_SAMPLE(false)
+                }
 #undef FB_MS_SAMPLE
             }
         }
     }
+    __syncthreads();                              // last chunk consumed: the slab now carries the leaders' results
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        const int x = threadIdx.x + k * blockDim.x;
+        if (x < W && leader[k] == x) slab[x] = make_float4(ar[k], ag[k], ab[k], 0.f);
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
         const int x = threadIdx.x + k * blockDim.x;
         if (x >= W) continue;
+        if (leader[k] != x) { const float4 v = slab[leader[k]]; ar[k] = v.x; ag[k] = v.y; ab[k] = v.z; }
         const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
         dMS[o] = pack_half4(ar[k], ag[k], ab[k], 0.f);                                  // multiple_scattering.comp:91
         const F pr = A<F>::RayleighPhase(F(nuf[k]));                                    // :92
