@@ -296,42 +296,51 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
 
     A<F> a(P);
     // ---- texel geometry, exact (scattering_density.comp:28-32) ------------------------------------------
+    // One evaluation per thread: thread t < TT takes texel t of the tile; r and mu (functions of y, z only) come out of
+    // the same call, the remaining threads (and padding texels of a partial tile) evaluate texel 0 of the row for them.
     F r, mu;
-    for (int t = tid; t < TT; t += NWARPS * 32) {
-        const int nui = t / dd.ms_tile, msl = t % dd.ms_tile;
+    {
+        const int t = tid < TT ? tid : 0;
+        const int nui = t >> dd.ms_shift, msl = t & (dd.ms_tile - 1);
         const int ms = tile * dd.ms_tile + msl;
-        float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (ms < P.scattering_mu_s_size) {
-            F mu_s, nu;
-            bool hu;
-            a.TexelToRMuMuSNu((unsigned)(nui * P.scattering_mu_s_size + ms), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hu);
-            F ox = f_sqrt(F(1.f) - mu * mu);
-            F sx = ox == F(0.f) ? F(0.f) : (nu - mu * mu_s) / ox;
-            F sy = f_sqrt(f_max(F(1.f) - sx * sx - mu_s * mu_s, F(0.f)));
-            g = make_float4(sx.v, sy.v, mu_s.v, __int_as_float(msl * dd.nu * ENT_B));   // .w: byte offset of the texel's rows
-        }
-        geoS[t] = g;
-    }
-    {   // r and mu of this CTA's row (independent of x)
-        F ms_u, nu_u;
+        const bool valid = tid < TT && ms < P.scattering_mu_s_size;
+        F mu_s, nu;
         bool hu;
-        a.TexelToRMuMuSNu(0u, (unsigned)y, (unsigned)z, r, mu, ms_u, nu_u, hu);
+        a.TexelToRMuMuSNu(valid ? (unsigned)(nui * P.scattering_mu_s_size + ms) : 0u, (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hu);
+        if (tid < TT) {
+            float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            if (valid) {
+                F ox = f_sqrt(F(1.f) - mu * mu);
+                F sx = ox == F(0.f) ? F(0.f) : (nu - mu * mu_s) / ox;
+                F sy = f_sqrt(f_max(F(1.f) - sx * sx - mu_s * mu_s, F(0.f)));
+                g = make_float4(sx.v, sy.v, mu_s.v, __int_as_float(msl * dd.nu * ENT_B));   // .w: byte offset of the texel's rows
+            }
+            geoS[tid] = g;
+        }
     }
     // ---- the 512 phase weights of this (r, mu) row, once per CTA (scattering_density.comp:93-103) -------
+    // Phase functions are smooth and well-conditioned: contracted fp32 with x^-1.5 = rsqrt(x)^3, the form the order-2
+    // samples use for nu1 (util.h:26-34).  The density profiles stay exact.
     {
-        const F ox = f_sqrt(F(1.f) - mu * mu);
+        const float ox = f_sqrt(F(1.f) - mu * mu).v, muf = mu.v;
         const F ray_rho = A<F>::ProfileDensity(P.rayleigh_density, r - a.bottom());
         const F mie_rho = A<F>::ProfileDensity(P.mie_density, r - a.bottom());
-        const F dphi = F(FB_PI_F) / F(16.f), dtheta = F(FB_PI_F) / F(16.f);
+        const float dd_ = (F(FB_PI_F) / F(16.f) * (F(FB_PI_F) / F(16.f))).v;        // dtheta * dphi
+        const float g = P.mie_phase_function_g;
+        const float kRw = 3.f / (16.f * FB_PI_F), kMw = 3.f / (8.f * FB_PI_F) * (1.f - g * g) / (2.f + g * g);
+        const float g2p1w = 1.f + g * g, m2gw = -2.f * g;
+        const float rr_ = P.rayleigh_scattering[0] * ray_rho.v, rg_ = P.rayleigh_scattering[1] * ray_rho.v,
+                    rb_ = P.rayleigh_scattering[2] * ray_rho.v;
+        const float mr_ = P.mie_scattering[0] * mie_rho.v, mg_ = P.mie_scattering[1] * mie_rho.v, mb_ = P.mie_scattering[2] * mie_rho.v;
         for (int e = tid; e < DL * 32; e += NWARPS * 32) {
             const int l = e >> 5, m = e & 31;
-            const F st = F(tg.st16[l]), ct = F(tg.ct16[l]);
-            const F wix = F(tg.cp32[m]) * st, wiy = F(tg.sp32[m]) * st;
-            const F nu2 = ox * wix + F(0.f) * wiy + mu * ct;
-            const F dw = dtheta * dphi * st;
-            const F pr = A<F>::RayleighPhase(nu2), pm = A<F>::MiePhase(F(P.mie_phase_function_g), nu2);
-            V w = (V(P.rayleigh_scattering) * ray_rho * pr + V(P.mie_scattering) * mie_rho * pm) * dw;
-            WtS[e] = make_float4(w.x.v, w.y.v, w.z.v, 0.f);
+            const float st = tg.st16[l], ct = tg.ct16[l];
+            const float nu2 = fmaf(ox, tg.cp32[m] * st, muf * ct);
+            const float dw = dd_ * st;
+            const float pr = fmaf(nu2 * kRw, nu2, kRw) * dw;
+            const float rs = rsqrt_fast(fmaf(m2gw, nu2, g2p1w));
+            const float pm = fmaf(nu2 * kMw, nu2, kMw) * (rs * rs * rs) * dw;
+            WtS[e] = make_float4(fmaf(rr_, pr, mr_ * pm), fmaf(rg_, pr, mg_ * pm), fmaf(rb_, pr, mb_ * pm), 0.f);
         }
     }
     uint32_t gmask = 0;                                                        // theta rows that reach the ground (CTA-uniform)
@@ -508,7 +517,12 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     // [k, k + 1) except when a knot lies between them, and on a segment L(a) + L(b) = 2 (intercept + slope * mean):
     // one table entry serves two samples.  The warp checks `same segment` per step and otherwise gives each sample its
     // own entry, so the result is the general body's up to summation order.
+#ifndef FB_PAIR_UNROLL
+#define FB_PAIR_UNROLL 1
+#endif
+    constexpr int PU = FB_PAIR_UNROLL;
     if (PAIRED)
+#pragma unroll PU
     for (int i = warp; 2 * i < nPair; i += NWARPS) {
         const int idx = 2 * i + (lane >> 4);
         const bool valid = idx < nPair;                                          // odd count: the last half-warp idles
