@@ -857,9 +857,11 @@ struct SingleNode {      // per trapezoid node, block-uniform; four 16-byte word
 // sun-angle cosine at the node, its u coordinate in the transmittance table, the bilinear blend, the smoothstep —
 // is a smooth, positive, well-conditioned chain and runs in contracted fp32 with MUFU reciprocal / square root.
 __global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
-                                                           uint2* __restrict__ dM, uint2* __restrict__ S, int r0) {
+                                                           uint2* __restrict__ dM, uint2* __restrict__ S, int r0, int CH) {
     __shared__ SingleNode nodes[NS];
     __shared__ float s_dx;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* slab = reinterpret_cast<float4*>(smem_raw);   // [CH][transmittance_mu_size]: per node, the row pair pre-blended
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = r0 + blockIdx.z;
     A<F> a(P);
@@ -867,62 +869,99 @@ __global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant
     bool hits;
     a.TexelToRMuMuSNu((unsigned)min(x, W - 1), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);
     const F H = f_sqrt(a.top() * a.top() - a.bottom() * a.bottom());
-    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+    // two threads per node (i and 64 + i): the transmittance look-up of GetTransmittance(r, mu, d_i) and the r_d-only
+    // terms are independent halves of the CTA's serial prologue
+    const bool split = blockDim.x >= 128;
+    for (int j = threadIdx.x; j < (split ? 128 : NS); j += blockDim.x) {
+        const int i = split ? (j & 63) : j;
+        if (i >= NS) continue;
+        const bool partA = !split || j < 64, partB = !split || j >= 64;
         const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);
         const F d = F((float)i) * dx;
-        const F r_d = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));      // single_scattering.comp:16
-        const V tr = a.Transmittance(T, r, mu, d, hits);                                // :19-21
-        SingleNode n;
-        n.g0 = make_float4(d.v, (F(1.f) / r_d).v, r_d.v, (r_d * r_d).v);
-        // GetTransmittanceToSun(r_d, .) and GetTransmittanceTextureUvFromRMu(r_d, .): the r_d-only parts
-        const F rho = A<F>::SafeSqrt(r_d * r_d - a.bottom() * a.bottom());              // transmittance.h:14
-        const F d_min = a.top() - r_d, d_max = rho + H;
-        const F v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size);               // transmittance.h:21-23
-        int y0, y1;
-        F fy;
-        tex_axis(v, P.transmittance_r_size, y0, y1, fy);
-        n.row0 = y0 * P.transmittance_mu_size; n.row1 = y1 * P.transmittance_mu_size;
-        const F sin_h = a.bottom() / r_d;                                               // transmittance.h:67-73
-        const F cos_h = -f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)));
-        const F al = F(P.sun_angular_radius);
-        const F e0 = -sin_h * al, e1 = sin_h * al;
-        n.g1 = make_float4(d_min.v, (F(1.f) / (d_max - d_min)).v, (cos_h + e0).v, (F(1.f) / (e1 - e0)).v);
-        n.t = make_float4(tr.x.v, tr.y.v, tr.z.v, fy.v);
-        const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);                         // a power of two: folding it is exact
-        n.rho_r = (A<F>::ProfileDensity(P.rayleigh_density, r_d - a.bottom()) * w).v;   // :24-27
-        n.rho_m = (A<F>::ProfileDensity(P.mie_density, r_d - a.bottom()) * w).v;
-        nodes[i] = n;
-        if (i == 0) s_dx = dx.v;
+        if (partA) {
+            const V tr = a.Transmittance(T, r, mu, d, hits);                            // :19-21
+            nodes[i].t.x = tr.x.v; nodes[i].t.y = tr.y.v; nodes[i].t.z = tr.z.v;
+            if (i == 0) s_dx = dx.v;
+        }
+        if (partB) {
+            const F r_d = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));  // single_scattering.comp:16
+            nodes[i].g0 = make_float4(d.v, (F(1.f) / r_d).v, r_d.v, (r_d * r_d).v);
+            // GetTransmittanceToSun(r_d, .) and GetTransmittanceTextureUvFromRMu(r_d, .): the r_d-only parts
+            const F rho = A<F>::SafeSqrt(r_d * r_d - a.bottom() * a.bottom());          // transmittance.h:14
+            const F d_min = a.top() - r_d, d_max = rho + H;
+            const F v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size);           // transmittance.h:21-23
+            int y0, y1;
+            F fy;
+            tex_axis(v, P.transmittance_r_size, y0, y1, fy);
+            nodes[i].row0 = y0 * P.transmittance_mu_size; nodes[i].row1 = y1 * P.transmittance_mu_size;
+            const F sin_h = a.bottom() / r_d;                                           // transmittance.h:67-73
+            const F cos_h = -f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)));
+            const F al = F(P.sun_angular_radius);
+            const F e0 = -sin_h * al, e1 = sin_h * al;
+            nodes[i].g1 = make_float4(d_min.v, (F(1.f) / (d_max - d_min)).v, (cos_h + e0).v, (F(1.f) / (e1 - e0)).v);
+            nodes[i].t.w = fy.v;
+            const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);                     // a power of two: folding it is exact
+            nodes[i].rho_r = (A<F>::ProfileDensity(P.rayleigh_density, r_d - a.bottom()) * w).v;   // :24-27
+            nodes[i].rho_m = (A<F>::ProfileDensity(P.mie_density, r_d - a.bottom()) * w).v;
+        }
     }
-    __syncthreads();
-    if (x >= W) return;
+    const bool active = x < W;
     const float r_mu_s = (r * mu_s).v, nuf = nu.v, tt = P.top_radius * P.top_radius;
-    const float un = (float)(P.transmittance_mu_size - 1);                              // u*N - 0.5 == x_mu * (N - 1)
+    const int TW = P.transmittance_mu_size;
+    const float un = (float)(TW - 1);                                                   // u*N - 0.5 == x_mu * (N - 1)
     const float umax = __int_as_float(__float_as_int(un) - 1);
     float rsr = 0.f, rsg = 0.f, rsb = 0.f, msr = 0.f, msg = 0.f, msb = 0.f;
+    // GetTransmittanceToSun(r_d, mu_s_d) reads the two table rows bracketing r_d -- a per-NODE pair -- at a column that
+    // depends on the texel: the 32 lanes of a warp (32 mu_s values) spread over the whole row, 19 cache lines per
+    // load.  Per chunk of CH nodes the CTA therefore blends each node's row pair once (coalesced), folds in
+    // GetTransmittance(r, mu, d_i), and the per-sample look-up becomes two shared-memory taps.
+    for (int c0 = 0; c0 < NS; c0 += CH) {
+        const int cn = min(CH, NS - c0);
+        __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
+        for (int e0 = 0; e0 < cn; e0 += 3) {
+            for (int j = threadIdx.x; j < TW; j += blockDim.x) {
+                float4 ra[3], rb[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {     // 6 row loads in flight per thread
+                    const SingleNode& n = nodes[c0 + min(e0 + u, cn - 1)];
+                    ra[u] = __ldg(T.p + n.row0 + j); rb[u] = __ldg(T.p + n.row1 + j);
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    if (e0 + u < cn) {
+                        const float4 nt = nodes[c0 + e0 + u].t;
+                        slab[(e0 + u) * TW + j] = make_float4(fmaf(nt.w, rb[u].x - ra[u].x, ra[u].x) * nt.x, fmaf(nt.w, rb[u].y - ra[u].y, ra[u].y) * nt.y,
+                                                              fmaf(nt.w, rb[u].z - ra[u].z, ra[u].z) * nt.z, 0.f);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (active) {
 #pragma unroll 3
-    for (int i = 0; i < NS; ++i) {
-        const float4 g0 = nodes[i].g0, g1 = nodes[i].g1, nt = nodes[i].t;
-        const float mu_s_d = fminf(fmaxf(fmaf(g0.x, nuf, r_mu_s) * g0.y, -1.f), 1.f);   // :17
-        // DistanceToTopAtmosphereBoundary(r_d, mu_s_d), params.h:105-110
-        const float disc = fmaf(g0.w, fmaf(mu_s_d, mu_s_d, -1.f), tt);
-        const float dtop = fmaxf(fmaf(-g0.z, mu_s_d, sqrt_fast(fmaxf(disc, 0.f))), 0.f);
-        const float tu = fminf(fmaxf((dtop - g1.x) * g1.y * un, 0.f), umax);            // transmittance.h:20-22
-        const float tm = __fadd_rd(tu, 8388608.f);
-        const int j = __float_as_int(tm) - 0x4B000000;
-        const float fx = tu - (tm - 8388608.f);
-        const float4 a00 = __ldg(T.p + nodes[i].row0 + j), a10 = __ldg(T.p + nodes[i].row0 + j + 1);
-        const float4 a01 = __ldg(T.p + nodes[i].row1 + j), a11 = __ldg(T.p + nodes[i].row1 + j + 1);
-        float sm = fminf(fmaxf((mu_s_d - g1.z) * g1.w, 0.f), 1.f);                      // smoothstep, transmittance.h:71-73
-        sm = sm * sm * fmaf(-2.f, sm, 3.f);
-        const float b0r = fmaf(fx, a10.x - a00.x, a00.x), b0g = fmaf(fx, a10.y - a00.y, a00.y), b0b = fmaf(fx, a10.z - a00.z, a00.z);
-        const float b1r = fmaf(fx, a11.x - a01.x, a01.x), b1g = fmaf(fx, a11.y - a01.y, a01.y), b1b = fmaf(fx, a11.z - a01.z, a01.z);
-        const float tr_ = fmaf(nt.w, b1r - b0r, b0r) * sm * nt.x, tg_ = fmaf(nt.w, b1g - b0g, b0g) * sm * nt.y,
-                    tb_ = fmaf(nt.w, b1b - b0b, b0b) * sm * nt.z;
-        const float rr = nodes[i].rho_r, rm = nodes[i].rho_m;
-        rsr = fmaf(tr_, rr, rsr); rsg = fmaf(tg_, rr, rsg); rsb = fmaf(tb_, rr, rsb);
-        msr = fmaf(tr_, rm, msr); msg = fmaf(tg_, rm, msg); msb = fmaf(tb_, rm, msb);
+            for (int e = 0; e < cn; ++e) {
+                const int i = c0 + e;
+                const float4 g0 = nodes[i].g0, g1 = nodes[i].g1;
+                const float mu_s_d = fminf(fmaxf(fmaf(g0.x, nuf, r_mu_s) * g0.y, -1.f), 1.f);   // :17
+                // DistanceToTopAtmosphereBoundary(r_d, mu_s_d), params.h:105-110
+                const float disc = fmaf(g0.w, fmaf(mu_s_d, mu_s_d, -1.f), tt);
+                const float dtop = fmaxf(fmaf(-g0.z, mu_s_d, sqrt_fast(fmaxf(disc, 0.f))), 0.f);
+                const float tu = fminf(fmaxf((dtop - g1.x) * g1.y * un, 0.f), umax);            // transmittance.h:20-22
+                const float tm = __fadd_rd(tu, 8388608.f);
+                const int j = __float_as_int(tm) - 0x4B000000;
+                const float fx = tu - (tm - 8388608.f);
+                // (the 32 columns of a warp are irregularly spaced: ~2.2 wavefronts per ideal one; padding does not help)
+                const float4 p0 = slab[e * TW + j], p1 = slab[e * TW + j + 1];
+                float sm = fminf(fmaxf((mu_s_d - g1.z) * g1.w, 0.f), 1.f);                      // smoothstep, transmittance.h:71-73
+                sm = sm * sm * fmaf(-2.f, sm, 3.f);
+                const float tr_ = fmaf(fx, p1.x - p0.x, p0.x) * sm, tg_ = fmaf(fx, p1.y - p0.y, p0.y) * sm, tb_ = fmaf(fx, p1.z - p0.z, p0.z) * sm;
+                const float rr = nodes[i].rho_r, rm = nodes[i].rho_m;
+                rsr = fmaf(tr_, rr, rsr); rsg = fmaf(tg_, rr, rsg); rsb = fmaf(tb_, rr, rsb);
+                msr = fmaf(tr_, rm, msr); msg = fmaf(tg_, rm, msg); msb = fmaf(tb_, rm, msb);
+            }
+        }
     }
+    if (!active) return;
     const F dx = F(s_dx);
     const V ray = V(F(rsr), F(rsg), F(rsb)) * dx * V(P.solar_irradiance) * V(P.rayleigh_scattering);   // :62-64
     const V mie = V(F(msr), F(msg), F(msb)) * dx * V(P.solar_irradiance) * V(P.mie_scattering);
@@ -936,7 +975,14 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
     const int nt = W >= 256 ? 256 : ((W + 31) / 32) * 32;
     dim3 g((W + nt - 1) / nt, c.P.scattering_mu_size, r1 - r0);
-    k_single_scattering<<<g, nt, 0, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0);
+    const int TW = c.P.transmittance_mu_size;
+    int CH = 3072 / TW;                           // nodes staged per pass: CH * TW * 16 B <= 48 KiB
+    CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
+    const size_t smem = (size_t)CH * TW * sizeof(float4);
+    if (smem > 160 * 1024) return ref::single_scattering(c, r0, r1);
+    cudaError_t e = cudaFuncSetAttribute(k_single_scattering, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_single_scattering<<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, CH);
     return cudaGetLastError();
 }
 
@@ -1020,27 +1066,36 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : 1) k_multip
             }
         }
     }
-    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+    // node records: the transmittance half and the (mu, r)-cell half of a node are independent, so two threads share a
+    // node (threads i and 64 + i when the CTA has them): the serial prologue of the 51 node threads is the CTA's
+    // critical path
+    const bool split = blockDim.x >= 128;
+    for (int j = threadIdx.x; j < (split ? 128 : NS); j += blockDim.x) {
+        const int i = split ? (j & 63) : j;
+        if (i >= NS) continue;
+        const bool partA = !split || j < 64, partB = !split || j >= 64;
         const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);                        // multiple_scattering.comp:23-26
         const F d = F((float)i) * dx;
-        const F r_i = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));      // :35-37
-        const F mu_i = A<F>::ClampCosine((r * mu + d) / r_i);
-        const V tr = a.Transmittance(T, r, mu, d, hits) * dx;                           // :45-48
-        const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);
-        F uvwz[4];
-        a.ScatteringUvwz(r_i, mu_i, F(0.f), F(0.f), hits, uvwz);                        // u_mu, u_r of scattering.h:7-60
-        int y0, y1, z0, z1;
-        F fy, fz;
-        tex_axis(uvwz[2], P.scattering_mu_size, y0, y1, fy);
-        tex_axis(uvwz[3], P.scattering_r_size, z0, z1, fz);
-        const float gy = 1.f - fy.v, gz = 1.f - fz.v;
-        MultiNode n;
-        n.w = make_float4(gy * gz, fy.v * gz, gy * fz.v, fy.v * fz.v);
-        n.off = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W), (unsigned)((z0 * P.scattering_mu_size + y1) * W),
-                           (unsigned)((z1 * P.scattering_mu_size + y0) * W), (unsigned)((z1 * P.scattering_mu_size + y1) * W));
-        n.t = make_float4((tr.x * w).v, (tr.y * w).v, (tr.z * w).v, d.v);
-        n.inv_r = (F(1.f) / r_i).v; n.pad0 = n.pad1 = n.pad2 = 0.f;
-        nodes[i] = n;
+        if (partA) {
+            const V tr = a.Transmittance(T, r, mu, d, hits) * dx;                       // :45-48
+            const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);
+            nodes[i].t = make_float4((tr.x * w).v, (tr.y * w).v, (tr.z * w).v, d.v);
+        }
+        if (partB) {
+            const F r_i = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));  // :35-37
+            const F mu_i = A<F>::ClampCosine((r * mu + d) / r_i);
+            F uvwz[4];
+            a.ScatteringUvwz(r_i, mu_i, F(0.f), F(0.f), hits, uvwz);                    // u_mu, u_r of scattering.h:7-60
+            int y0, y1, z0, z1;
+            F fy, fz;
+            tex_axis(uvwz[2], P.scattering_mu_size, y0, y1, fy);
+            tex_axis(uvwz[3], P.scattering_r_size, z0, z1, fz);
+            const float gy = 1.f - fy.v, gz = 1.f - fz.v;
+            nodes[i].w = make_float4(gy * gz, fy.v * gz, gy * fz.v, fy.v * fz.v);
+            nodes[i].off = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W), (unsigned)((z0 * P.scattering_mu_size + y1) * W),
+                                      (unsigned)((z1 * P.scattering_mu_size + y0) * W), (unsigned)((z1 * P.scattering_mu_size + y1) * W));
+            nodes[i].inv_r = (F(1.f) / r_i).v; nodes[i].pad0 = nodes[i].pad1 = nodes[i].pad2 = 0.f;
+        }
     }
     // the mu_s mapping constants (scattering.h:48-56)
     const float bot = P.bottom_radius, top = P.top_radius;
