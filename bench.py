@@ -132,7 +132,7 @@ def ncu_dram_traffic():
         name, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for r in rows[2:]:
-            if "k_density_main" in r[name]:
+            if "k_density_main<0>" in r[name]:    # <0>: the order >= 3 instantiation
                 return {"bytes_per_launch": float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]],
                         "source": "profiles/r1_precompute_full_raw.csv (order >= 3 launch; tables are L2-resident)"}
     except (OSError, ValueError, KeyError, IndexError):

@@ -856,6 +856,7 @@ struct SingleNode {      // per trapezoid node, block-uniform; four 16-byte word
 // horizon terms, the table rows bracketing r_d) are exact (xf, as written).  The per-texel-per-node remainder — the
 // sun-angle cosine at the node, its u coordinate in the transmittance table, the bilinear blend, the smoothstep —
 // is a smooth, positive, well-conditioned chain and runs in contracted fp32 with MUFU reciprocal / square root.
+template <bool STAGED>   // STAGED: row pairs pre-blended in shared memory (pays when a CTA covers at least one table row of texels)
 __global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
                                                            uint2* __restrict__ dM, uint2* __restrict__ S, int r0, int CH) {
     __shared__ SingleNode nodes[NS];
@@ -915,6 +916,33 @@ __global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant
     // depends on the texel: the 32 lanes of a warp (32 mu_s values) spread over the whole row, 19 cache lines per
     // load.  Per chunk of CH nodes the CTA therefore blends each node's row pair once (coalesced), folds in
     // GetTransmittance(r, mu, d_i), and the per-sample look-up becomes two shared-memory taps.
+    if (!STAGED) {                                // direct look-ups: 4 global taps per sample
+        __syncthreads();
+        if (active) {
+#pragma unroll 3
+            for (int i = 0; i < NS; ++i) {
+                const float4 g0 = nodes[i].g0, g1 = nodes[i].g1, nt = nodes[i].t;
+                const float mu_s_d = fminf(fmaxf(fmaf(g0.x, nuf, r_mu_s) * g0.y, -1.f), 1.f);   // :17
+                const float disc = fmaf(g0.w, fmaf(mu_s_d, mu_s_d, -1.f), tt);                  // params.h:105-110
+                const float dtop = fmaxf(fmaf(-g0.z, mu_s_d, sqrt_fast(fmaxf(disc, 0.f))), 0.f);
+                const float tu = fminf(fmaxf((dtop - g1.x) * g1.y * un, 0.f), umax);            // transmittance.h:20-22
+                const float tm = __fadd_rd(tu, 8388608.f);
+                const int j = __float_as_int(tm) - 0x4B000000;
+                const float fx = tu - (tm - 8388608.f);
+                const float4 a00 = __ldg(T.p + nodes[i].row0 + j), a10 = __ldg(T.p + nodes[i].row0 + j + 1);
+                const float4 a01 = __ldg(T.p + nodes[i].row1 + j), a11 = __ldg(T.p + nodes[i].row1 + j + 1);
+                float sm = fminf(fmaxf((mu_s_d - g1.z) * g1.w, 0.f), 1.f);                      // smoothstep, transmittance.h:71-73
+                sm = sm * sm * fmaf(-2.f, sm, 3.f);
+                const float b0r = fmaf(fx, a10.x - a00.x, a00.x), b0g = fmaf(fx, a10.y - a00.y, a00.y), b0b = fmaf(fx, a10.z - a00.z, a00.z);
+                const float b1r = fmaf(fx, a11.x - a01.x, a01.x), b1g = fmaf(fx, a11.y - a01.y, a01.y), b1b = fmaf(fx, a11.z - a01.z, a01.z);
+                const float tr_ = fmaf(nt.w, b1r - b0r, b0r) * sm * nt.x, tg_ = fmaf(nt.w, b1g - b0g, b0g) * sm * nt.y,
+                            tb_ = fmaf(nt.w, b1b - b0b, b0b) * sm * nt.z;
+                const float rr = nodes[i].rho_r, rm = nodes[i].rho_m;
+                rsr = fmaf(tr_, rr, rsr); rsg = fmaf(tg_, rr, rsg); rsb = fmaf(tb_, rr, rsb);
+                msr = fmaf(tr_, rm, msr); msg = fmaf(tg_, rm, msg); msb = fmaf(tb_, rm, msb);
+            }
+        }
+    } else
     for (int c0 = 0; c0 < NS; c0 += CH) {
         const int cn = min(CH, NS - c0);
         __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
@@ -979,10 +1007,14 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     int CH = 3072 / TW;                           // nodes staged per pass: CH * TW * 16 B <= 48 KiB
     CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
     const size_t smem = (size_t)CH * TW * sizeof(float4);
-    if (smem > 160 * 1024) return ref::single_scattering(c, r0, r1);
-    cudaError_t e = cudaFuncSetAttribute(k_single_scattering, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // staging touches TW entries per node, the samples nt texels per node: stage when a CTA's texels cover the row
+    if (TW > nt || smem > 160 * 1024) {
+        k_single_scattering<false><<<g, nt, 0, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, 0);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(k_single_scattering<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_single_scattering<<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, CH);
+    k_single_scattering<true><<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, CH);
     return cudaGetLastError();
 }
 
