@@ -399,3 +399,72 @@ def test_default_dims_end_to_end_fast_vs_reference_family(default_tables, family
     check("transmittance fast-vs-reference", err32(default_tables["transmittance"], T))
     check("irradiance fast-vs-reference", err32(default_tables["irradiance"], E))
     check_compounded("scattering fast-vs-reference end to end", err16(default_tables["scattering"], S))
+
+
+def _clamped_runs(p, margin=1e-3):
+    """(r, mu, mu_s) columns of the scattering table with the number of nu knots that lie below / above the admissible
+    interval [mu mu_s - s, mu mu_s + s] by at least `margin` (scattering.h:62-137 in float64): such knots are clamped onto
+    the same bound, so their texels have identical inputs in every 3-D stage."""
+    NR, NMU, NMS, NNU = p.scattering_r_size, p.scattering_mu_size, p.scattering_mu_s_size, p.scattering_nu_size
+    bot, top = p.bottom_radius, p.top_radius
+    H = np.sqrt(top * top - bot * bot)
+    ufc = lambda u, n: (u - 0.5 / n) / (1 - 1.0 / n)
+    frag = lambda i, n: n * (0.5 / n + i / (n - 1) * (1 - 1.0 / n))
+    z, y, ms = np.arange(NR)[:, None, None], np.arange(NMU)[None, :, None], np.arange(NMS)[None, None, :]
+    rho = H * ufc(frag(z, NR) / NR, NR)
+    r = np.sqrt(rho * rho + bot * bot)
+    u_mu = frag(y, NMU) / NMU
+    with np.errstate(all="ignore"):
+        d1 = (r - bot) + (rho - (r - bot)) * ufc(1 - 2 * u_mu, NMU // 2)
+        mu1 = np.where(d1 == 0, -1.0, np.clip(-(rho * rho + d1 * d1) / (2 * r * d1), -1, 1))
+        d2 = (top - r) + (rho + H - (top - r)) * ufc(2 * u_mu - 1, NMU // 2)
+        mu2 = np.where(d2 == 0, 1.0, np.clip((H * H - rho * rho - d2 * d2) / (2 * r * d2), -1, 1))
+    mu = np.where(u_mu < 0.5, mu1, mu2)
+    A = -2 * p.mu_s_min * bot / (H - (top - bot))
+    xm = ufc(frag(ms, NNU * NMS) / NMS, NMS)          # nu slice 0: f_mu_s = fx
+    a = (A - xm * A) / (1 + xm * A)
+    d = (top - bot) + np.minimum(a, A) * (H - (top - bot))
+    mus = np.where(d == 0, 1.0, np.clip((H * H - d * d) / (2 * bot * d), -1, 1))
+    s = np.sqrt((1 - mu * mu) * (1 - mus * mus))
+    knots = (2.0 * np.arange(NNU) / (NNU - 1) - 1.0)[None, None, None, :]
+    below = (knots < (mu * mus - s)[..., None] - margin).sum(-1)
+    above = (knots > (mu * mus + s)[..., None] + margin).sum(-1)
+    return below, above
+
+
+def test_clamped_nu_runs_hold_identical_texels_and_runs_repeat(default_tables, builder):
+    """Domain property the duplicate-texel elimination rests on: nu knots clamped onto the same bound give identical
+    inputs, hence identical texels, in every 3-D stage (true of the shader, of both kernel families, of any correct
+    implementation).  And the product kernels are run-to-run identical (ordered compaction, per-lane corrections)."""
+    p = fb.Parameters()
+    below, above = _clamped_runs(p)
+    NMS, NNU = p.scattering_mu_s_size, p.scattering_nu_size
+    assert (below >= 2).mean() > 0.02 and (above >= 2).mean() > 0.02        # the property is exercised
+    names = ["delta_rayleigh", "delta_mie"] + [f"o{o}_{n}" for o in (2, 3, 4) for n in ("scattering_density", "delta_multiple_scattering")]
+    def same(a, b, what):
+        # mu_s is derived from each texel's own x coordinate and may differ in its last bit between nu slices: then the
+        # inputs are one ulp apart, not identical, and an output may round to the neighbouring fp16 value
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        assert np.all(np.abs(a - b) <= np.maximum(2.0 ** -24, 2.0 ** -10 * np.abs(b))), what
+        assert a.size == 0 or (a == b).mean() >= 0.99, what
+
+    for name in names:
+        tab = default_tables[name].reshape(p.scattering_r_size, p.scattering_mu_size, NNU, NMS, 4)
+        for k in range(1, NNU):
+            lo = below > k                                                   # knots 0 .. k all clamped onto the lower bound
+            same(tab[:, :, k][lo], tab[:, :, 0][lo], (name, "lower run", k))
+            hi = above > k                                                   # knots NNU-1-k .. NNU-1 onto the upper bound
+            same(tab[:, :, NNU - 1 - k][hi], tab[:, :, NNU - 1][hi], (name, "upper run", k))
+    # determinism: the same stage on the same inputs twice
+    pend = fb.Atmosphere.build(builder, None, p)
+    sync()
+    for stage, order, image in ((api.STAGE_SCATTERING_DENSITY, 2, api.IMAGE_SCATTERING_DENSITY),
+                                (api.STAGE_SCATTERING_DENSITY, 3, api.IMAGE_SCATTERING_DENSITY),
+                                (api.STAGE_MULTIPLE_SCATTERING, 0, api.IMAGE_DELTA_MULTIPLE_SCATTERING)):
+        outs = []
+        for _ in range(2):
+            pend.upload(image, np.full(pend._shape(image), 7.0, dtype=np.float16))   # poison: an unwritten texel shows up
+            pend.run_stage(stage, order=order)
+            outs.append(pend.download(image))
+        assert not np.any(outs[0][..., :3] == 7.0), (stage, order)
+        assert np.array_equal(outs[0], outs[1]), (stage, order)
