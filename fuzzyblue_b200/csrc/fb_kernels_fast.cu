@@ -1078,11 +1078,13 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : 1) k_multip
     // un-clamped texels (one slice, warp-uniformly) and followers, which wait for their leader's result.
     int leader[TPT];
     {
-        float* nuS = reinterpret_cast<float*>(slab);                     // aliases the slab: consumed before the first staging pass
+        // (nu, r mu_s) of every texel; aliases the slab: consumed before the first staging pass.  mu_s is derived from the
+        // texel's own x coordinate and may differ in its last bit between nu slices: both inputs must match bit for bit.
+        int2* nuS = reinterpret_cast<int2*>(slab);
 #pragma unroll
         for (int k = 0; k < TPT; ++k) {
             const int x = threadIdx.x + k * blockDim.x;
-            if (x < W) nuS[x] = nuf[k];
+            if (x < W) nuS[x] = make_int2(__float_as_int(nuf[k]), __float_as_int(rmus[k]));
         }
         __syncthreads();
 #pragma unroll
@@ -1090,10 +1092,10 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : 1) k_multip
             const int x = threadIdx.x + k * blockDim.x;
             leader[k] = x;
             if (x < W) {
-                const int me = __float_as_int(nuf[k]);
+                const int2 me = make_int2(__float_as_int(nuf[k]), __float_as_int(rmus[k]));
                 int lo = x, hi = x;
-                while (lo >= MS && __float_as_int(nuS[lo - MS]) == me) lo -= MS;
-                while (hi + MS < W && __float_as_int(nuS[hi + MS]) == me) hi += MS;
+                while (lo >= MS && nuS[lo - MS].x == me.x && nuS[lo - MS].y == me.y) lo -= MS;
+                while (hi + MS < W && nuS[hi + MS].x == me.x && nuS[hi + MS].y == me.y) hi += MS;
                 leader[k] = lo < MS ? lo : hi;
             }
         }
