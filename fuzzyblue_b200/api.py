@@ -81,6 +81,13 @@ assert ctypes.sizeof(FbParams) == 320 and ctypes.sizeof(FbDrawParams) == 92
 
 # every symbol include/fuzzyblue.h declares: name -> (restype, argtypes)
 _P = POINTER
+class FbExportLayout(ctypes.Structure):
+    """Where the three tables sit in an exported allocation (include/fuzzyblue.h: FbExportLayout)."""
+    _fields_ = [("allocation_bytes", c_size_t), ("scattering_offset", c_size_t), ("scattering_bytes", c_size_t),
+                ("transmittance_offset", c_size_t), ("transmittance_bytes", c_size_t),
+                ("irradiance_offset", c_size_t), ("irradiance_bytes", c_size_t)]
+
+
 ABI = {
     "fb_status_string": (c_char_p, [c_int]),
     "fb_last_error": (c_char_p, []),
@@ -127,6 +134,13 @@ ABI = {
     "fb_sky_radiance": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]),
     "fb_sun_and_sky_irradiance": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]),
     "fb_atmosphere_build_batch": (c_int, [c_void_p, _P(FbParams), c_uint32, c_uint32, c_void_p, _P(c_void_p)]),
+    "fb_builder_set_exportable": (c_int, [c_void_p, c_int]),
+    "fb_atmosphere_export_fd": (c_int, [c_void_p, _P(c_int), _P(FbExportLayout)]),
+    "fb_external_memory_read_fd": (c_int, [c_int, c_int, c_size_t, c_size_t, c_void_p, c_size_t]),
+    "fb_external_semaphore_import_fd": (c_int, [c_int, c_int, c_int, _P(c_void_p)]),
+    "fb_external_semaphore_signal": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "fb_external_semaphore_wait": (c_int, [c_void_p, c_uint64, c_void_p]),
+    "fb_external_semaphore_destroy": (None, [c_void_p]),
 }
 
 _LIB = None
@@ -300,6 +314,10 @@ class Builder:
     def set_kernels(self, kernels: int):
         _check(_lib().fb_builder_set_kernels(self._h, kernels))
 
+    def set_exportable(self, on: bool = True):
+        """Atmospheres built afterwards keep their tables in an fd-exportable allocation (Vulkan interop)."""
+        _check(_lib().fb_builder_set_exportable(self._h, 1 if on else 0))
+
     def trim(self):
         """Return cached device blocks of finished precomputes to the driver."""
         _check(_lib().fb_builder_trim(self._h))
@@ -404,6 +422,13 @@ class Atmosphere:
     def read_irradiance(self, stream=None) -> np.ndarray:
         w, h = self.irradiance_extent()
         return _read(_lib().fb_atmosphere_read_irradiance, self._h, (h, w, 4), np.float32, stream)
+
+    def export_fd(self):
+        """(fd, FbExportLayout) of the block holding the three tables — what a Vulkan caller imports as OPAQUE_FD
+        device memory in place of the ``vk::Image`` getters (precompute.rs:2075-2101).  The caller owns ``fd``."""
+        fd, lay = c_int(-1), FbExportLayout()
+        _check(_lib().fb_atmosphere_export_fd(self._h, byref(fd), byref(lay)))
+        return fd.value, lay
 
     def close(self):
         if self._h and self._owned:
@@ -578,3 +603,10 @@ def sun_and_sky_irradiance(atmosphere: Atmosphere, point, normal, sun_direction,
     """GetSunAndSkyIrradiance (shaders/render_lighting.h:10-28) for n queries."""
     _check(_lib().fb_sun_and_sky_irradiance(atmosphere._h, _ptr(point), _ptr(normal), _ptr(sun_direction), n, _ptr(sun_out),
                                             _ptr(sky_out), _stream(stream)))
+
+
+def external_memory_read(device: int, fd: int, allocation_bytes: int, offset: int, shape, dtype) -> np.ndarray:
+    """Import an exported allocation as a consumer would (here: CUDA is the importer) and copy one table out."""
+    out = np.empty(shape, dtype=dtype)
+    _check(_lib().fb_external_memory_read_fd(device, fd, allocation_bytes, offset, out.ctypes.data_as(c_void_p), out.nbytes))
+    return out

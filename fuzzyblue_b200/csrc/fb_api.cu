@@ -4,6 +4,7 @@
 //
 // There is no CPU fallback anywhere in this file: without a CUDA device fb_builder_create fails
 // with FB_ERR_NO_DEVICE and nothing else can be constructed.
+#include <cuda.h>           // driver-API TYPES only (virtual memory management); entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -195,10 +196,96 @@ struct BlockCache {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Exportable device memory: the kept block as a CUDA virtual-memory allocation whose POSIX
+// file descriptor a Vulkan caller imports (VkImportMemoryFdInfoKHR, OPAQUE_FD) — the counterpart of
+// Atmosphere::{transmittance,scattering,irradiance}() handing out vk::Image (precompute.rs:2075-2101).  The driver
+// entry points are fetched at run time, so the library carries no link-time dependency on libcuda.
+// ---------------------------------------------------------------------------------------------
+struct Vmm {
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+    CUresult (*Release)(CUmemGenericAllocationHandle);
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+    CUresult (*AddressFree)(CUdeviceptr, size_t);
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    CUresult (*Unmap)(CUdeviceptr, size_t);
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+    CUresult (*Export)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+    CUresult (*Import)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
+    bool ok;
+};
+static const Vmm& vmm_api() {
+    static Vmm v = [] {
+        Vmm t;
+        std::memset(&t, 0, sizeof t);
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        t.ok = get("cuMemGetAllocationGranularity", (void**)&t.GetGranularity) && get("cuMemCreate", (void**)&t.Create) &&
+               get("cuMemRelease", (void**)&t.Release) && get("cuMemAddressReserve", (void**)&t.AddressReserve) &&
+               get("cuMemAddressFree", (void**)&t.AddressFree) && get("cuMemMap", (void**)&t.Map) &&
+               get("cuMemUnmap", (void**)&t.Unmap) && get("cuMemSetAccess", (void**)&t.SetAccess) &&
+               get("cuMemExportToShareableHandle", (void**)&t.Export) && get("cuMemImportFromShareableHandle", (void**)&t.Import);
+        (void)cudaGetLastError();
+        return t;
+    }();
+    return v;
+}
+static CUmemAllocationProp vmm_prop(int device) {
+    CUmemAllocationProp prop;
+    std::memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+// map `handle` (size bytes) read-write on `device`; 0 on failure
+static CUdeviceptr vmm_map(const Vmm& v, int device, CUmemGenericAllocationHandle handle, size_t size) {
+    CUdeviceptr ptr = 0;
+    if (v.AddressReserve(&ptr, size, 0, 0, 0) != CUDA_SUCCESS) return 0;
+    if (v.Map(ptr, size, 0, handle, 0) != CUDA_SUCCESS) { v.AddressFree(ptr, size); return 0; }
+    CUmemAccessDesc acc;
+    std::memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (v.SetAccess(ptr, size, &acc, 1) != CUDA_SUCCESS) { v.Unmap(ptr, size); v.AddressFree(ptr, size); return 0; }
+    return ptr;
+}
+static bool vmm_alloc(int device, size_t bytes, void** out, unsigned long long* handle, size_t* alloc_bytes) {
+    const Vmm& v = vmm_api();
+    if (!v.ok) return false;
+    (void)cudaFree(0);                               // make sure the primary context exists and is current
+    const CUmemAllocationProp prop = vmm_prop(device);
+    size_t gran = 0;
+    if (v.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || !gran) return false;
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h;
+    if (v.Create(&h, size, &prop, 0) != CUDA_SUCCESS) return false;
+    const CUdeviceptr ptr = vmm_map(v, device, h, size);
+    if (!ptr) { v.Release(h); return false; }
+    *out = reinterpret_cast<void*>(ptr);
+    *handle = (unsigned long long)h;
+    *alloc_bytes = size;
+    return true;
+}
+static void vmm_free(void* p, unsigned long long handle, size_t alloc_bytes) {
+    const Vmm& v = vmm_api();
+    if (!v.ok || !p) return;
+    (void)cudaDeviceSynchronize();                   // cudaFree semantics: nothing may still be using the block
+    v.Unmap((CUdeviceptr)p, alloc_bytes);
+    v.AddressFree((CUdeviceptr)p, alloc_bytes);
+    v.Release((CUmemGenericAllocationHandle)handle);
+}
+
 struct FbBuilder {
     int device;
     int sm_count;
     int kernels;
+    int exportable;          // kept blocks come from the virtual-memory API as fd-exportable allocations
     Trig trig;
     std::shared_ptr<BlockCache> cache;
 };
@@ -209,6 +296,10 @@ struct FbAtmosphere {
     std::shared_ptr<BlockCache> cache;
     void* block;             // one device block: [scattering | transmittance | irradiance]
     size_t block_bytes;
+    bool vmm;                // block is an exportable virtual-memory allocation (not from the cache)
+    unsigned long long vmm_handle;
+    size_t vmm_bytes;        // allocation size (block_bytes rounded up to the granularity)
+    size_t off_transmittance, off_irradiance;
     FbParams P;
     float4* transmittance;
     float4* irradiance;
@@ -301,6 +392,7 @@ int fb_builder_create(int device, FbBuilder** out) {
     b->device = device;
     b->sm_count = prop.multiProcessorCount;
     b->kernels = FB_KERNELS_FAST;
+    b->exportable = 0;
     b->cache = std::make_shared<BlockCache>(device);
     make_trig(&b->trig);
     *out = b;
@@ -324,6 +416,100 @@ int fb_builder_trim(FbBuilder* b) {
     b->cache->trim();
     return FB_OK;
 }
+int fb_builder_set_exportable(FbBuilder* b, int on) {
+    if (!b) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_set_exportable: NULL");
+    if (on && !vmm_api().ok) return fail(FB_ERR_CUDA, "fb_builder_set_exportable: the driver lacks the virtual memory management API");
+    b->exportable = on ? 1 : 0;
+    return FB_OK;
+}
+
+int fb_atmosphere_export_fd(const FbAtmosphere* a, int* fd, FbExportLayout* layout) {
+    if (!a || !fd) return fail(FB_ERR_INVALID_ARGUMENT, "fb_atmosphere_export_fd: NULL");
+    *fd = -1;
+    if (!a->vmm) return fail(FB_ERR_INVALID_ARGUMENT, "fb_atmosphere_export_fd: build the atmosphere after fb_builder_set_exportable(b, 1)");
+    DeviceGuard g(a->device);
+    int out = -1;
+    const CUresult r = vmm_api().Export(&out, (CUmemGenericAllocationHandle)a->vmm_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (r != CUDA_SUCCESS) return fail(FB_ERR_CUDA, "cuMemExportToShareableHandle failed (" + std::to_string((int)r) + ")");
+    *fd = out;
+    if (layout) {
+        layout->allocation_bytes = a->vmm_bytes;
+        layout->scattering_offset = 0;
+        layout->scattering_bytes = bytes3d(a->P);
+        layout->transmittance_offset = a->off_transmittance;
+        layout->transmittance_bytes = image_bytes(a->P, FB_IMAGE_TRANSMITTANCE);
+        layout->irradiance_offset = a->off_irradiance;
+        layout->irradiance_bytes = image_bytes(a->P, FB_IMAGE_IRRADIANCE);
+    }
+    return FB_OK;
+}
+
+int fb_external_memory_read_fd(int device, int fd, size_t allocation_bytes, size_t offset, void* host, size_t bytes) {
+    if (fd < 0 || !host || offset + bytes > allocation_bytes) return fail(FB_ERR_INVALID_ARGUMENT, "fb_external_memory_read_fd");
+    const Vmm& v = vmm_api();
+    if (!v.ok) return fail(FB_ERR_CUDA, "the driver lacks the virtual memory management API");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(FB_ERR_CUDA, "cudaSetDevice failed");
+    (void)cudaFree(0);
+    CUmemGenericAllocationHandle h;
+    CUresult r = v.Import(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (r != CUDA_SUCCESS) return fail(FB_ERR_CUDA, "cuMemImportFromShareableHandle failed (" + std::to_string((int)r) + ")");
+    const CUdeviceptr ptr = vmm_map(v, device, h, allocation_bytes);
+    if (!ptr) { v.Release(h); return fail(FB_ERR_CUDA, "mapping the imported allocation failed"); }
+    const cudaError_t e = cudaMemcpy(host, reinterpret_cast<const char*>(ptr) + offset, bytes, cudaMemcpyDeviceToHost);
+    v.Unmap(ptr, allocation_bytes);
+    v.AddressFree(ptr, allocation_bytes);
+    v.Release(h);
+    return e == cudaSuccess ? FB_OK : cuda_fail(e, "cudaMemcpy from the imported allocation");
+}
+
+struct FbExternalSemaphore {
+    int device;
+    cudaExternalSemaphore_t sem;
+    int timeline;
+};
+int fb_external_semaphore_import_fd(int device, int fd, int is_timeline, FbExternalSemaphore** out) {
+    if (!out || fd < 0) return fail(FB_ERR_INVALID_ARGUMENT, "fb_external_semaphore_import_fd");
+    *out = nullptr;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(FB_ERR_CUDA, "cudaSetDevice failed");
+    cudaExternalSemaphoreHandleDesc d;
+    std::memset(&d, 0, sizeof d);
+    d.type = is_timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+    d.handle.fd = fd;                                // ownership of the descriptor passes to CUDA on success
+    cudaExternalSemaphore_t sem;
+    FB_CUDA(cudaImportExternalSemaphore(&sem, &d));
+    FbExternalSemaphore* s = new (std::nothrow) FbExternalSemaphore();
+    if (!s) { cudaDestroyExternalSemaphore(sem); return fail(FB_ERR_OUT_OF_MEMORY, "host allocation"); }
+    s->device = device; s->sem = sem; s->timeline = is_timeline ? 1 : 0;
+    *out = s;
+    return FB_OK;
+}
+int fb_external_semaphore_signal(FbExternalSemaphore* s, uint64_t value, void* stream) {
+    if (!s) return fail(FB_ERR_INVALID_ARGUMENT, "fb_external_semaphore_signal: NULL");
+    DeviceGuard g(s->device);
+    cudaExternalSemaphoreSignalParams p;
+    std::memset(&p, 0, sizeof p);
+    p.params.fence.value = s->timeline ? value : 0;
+    FB_CUDA(cudaSignalExternalSemaphoresAsync(&s->sem, &p, 1, (cudaStream_t)stream));
+    return FB_OK;
+}
+int fb_external_semaphore_wait(FbExternalSemaphore* s, uint64_t value, void* stream) {
+    if (!s) return fail(FB_ERR_INVALID_ARGUMENT, "fb_external_semaphore_wait: NULL");
+    DeviceGuard g(s->device);
+    cudaExternalSemaphoreWaitParams p;
+    std::memset(&p, 0, sizeof p);
+    p.params.fence.value = s->timeline ? value : 0;
+    FB_CUDA(cudaWaitExternalSemaphoresAsync(&s->sem, &p, 1, (cudaStream_t)stream));
+    return FB_OK;
+}
+void fb_external_semaphore_destroy(FbExternalSemaphore* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    cudaDestroyExternalSemaphore(s->sem);
+    delete s;
+}
+
 int fb_builder_device(const FbBuilder* b) { return b ? b->device : -1; }
 int fb_builder_sm_count(const FbBuilder* b) { return b ? b->sm_count : 0; }
 
@@ -342,7 +528,8 @@ static void free_pending_temps(FbPending* p) {
 void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
     if (!a) return;
     DeviceGuard g(a->device);
-    a->cache->put(a->block, a->block_bytes);
+    if (a->vmm) vmm_free(a->block, a->vmm_handle, a->vmm_bytes);
+    else a->cache->put(a->block, a->block_bytes);
     delete a;
 }
 
@@ -388,7 +575,19 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     p->img.scratch_bytes = fast::scratch_bytes(*params);
     a->block_bytes = b3 + b2t + b2e;
     p->temp_bytes = 4 * b3 + b2e + up(p->img.scratch_bytes);
-    cudaError_t e = b->cache->get(&a->block, a->block_bytes);
+    a->vmm = false; a->vmm_handle = 0; a->vmm_bytes = 0;
+    a->off_transmittance = b3; a->off_irradiance = b3 + b2t;
+    cudaError_t e = cudaSuccess;
+    if (b->exportable) {
+        if (!vmm_alloc(b->device, a->block_bytes, &a->block, &a->vmm_handle, &a->vmm_bytes)) {
+            a->block = nullptr;
+            fb_pending_destroy(p);
+            return fail(FB_ERR_CUDA, "exportable allocation failed (cuMemCreate with a POSIX file-descriptor handle type)");
+        }
+        a->vmm = true;
+    } else {
+        e = b->cache->get(&a->block, a->block_bytes);
+    }
     if (e == cudaSuccess) e = b->cache->get(&p->temp_block, p->temp_bytes);
     if (e != cudaSuccess) {
         fb_pending_destroy(p);

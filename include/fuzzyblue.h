@@ -200,6 +200,36 @@ FB_API int fb_atmosphere_read_irradiance(const FbAtmosphere* a, void* host, size
 /* Drop for Atmosphere, :1045-1073 */
 FB_API void fb_atmosphere_destroy(FbAtmosphere* a);
 
+/* ---- Vulkan interop (what keeps Atmosphere::{transmittance,scattering,irradiance}() -> vk::Image, :2075-2101, and the
+ * caller-chosen final layout / stage / access of Parameters, :691-698, meaningful for a Vulkan caller) ---------------
+ * After fb_builder_set_exportable(b, 1) the block an Atmosphere keeps (its three tables) is a CUDA virtual-memory
+ * allocation with a POSIX-file-descriptor handle.  fb_atmosphere_export_fd returns a NEW descriptor per call (the caller
+ * closes it, or hands it to vkAllocateMemory with VkImportMemoryFdInfoKHR { handleType = OPAQUE_FD }, which takes it
+ * over) and where each table sits in the allocation; the Vulkan side binds a VkBuffer to the imported memory and
+ * copies the tightly packed tables (layout at the top of this header) into its images with vkCmdCopyBufferToImage,
+ * choosing layout, stage and access itself.  Exportable blocks bypass the builder's block cache. */
+typedef struct FbExportLayout {
+    size_t allocation_bytes;                     /* size to pass as VkMemoryAllocateInfo::allocationSize */
+    size_t scattering_offset, scattering_bytes;  /* RGBA16F [r][mu][nu*mu_s] */
+    size_t transmittance_offset, transmittance_bytes; /* RGBA32F [r][mu] */
+    size_t irradiance_offset, irradiance_bytes;  /* RGBA32F [r][mu_s] */
+} FbExportLayout;
+FB_API int fb_builder_set_exportable(FbBuilder* b, int on);
+FB_API int fb_atmosphere_export_fd(const FbAtmosphere* a, int* fd, FbExportLayout* layout);
+/* What an importing process does, with CUDA as the importer: import `fd`, map it, copy `bytes` at `offset` to host
+ * memory, unmap.  Does not close `fd`.  Used by the tests to prove the exported allocation carries the tables. */
+FB_API int fb_external_memory_read_fd(int device, int fd, size_t allocation_bytes, size_t offset, void* host, size_t bytes);
+/* The caller's VkSemaphore (exported with VK_EXTERNAL_SEMAPHORE_HANDLE_TYPE_OPAQUE_FD_BIT; is_timeline = 1 for a
+ * timeline semaphore) as a stream operation: signal it after the precompute / wait for it before a draw, in place of
+ * the queue-family ownership transfer of PendingAtmosphere::acquire_ownership (:2147-2201).  On success the
+ * descriptor belongs to CUDA.  NOT exercised in this image (no Vulkan loader or ICD): thin wrappers over
+ * cudaImportExternalSemaphore / cudaSignalExternalSemaphoresAsync / cudaWaitExternalSemaphoresAsync. */
+typedef struct FbExternalSemaphore FbExternalSemaphore;
+FB_API int fb_external_semaphore_import_fd(int device, int fd, int is_timeline, FbExternalSemaphore** out);
+FB_API int fb_external_semaphore_signal(FbExternalSemaphore* s, uint64_t value, void* stream);
+FB_API int fb_external_semaphore_wait(FbExternalSemaphore* s, uint64_t value, void* stream);
+FB_API void fb_external_semaphore_destroy(FbExternalSemaphore* s);
+
 /* Host-buffer convenience = what a caller of the reference does end to end (build, submit, wait,
  * read back as examples/dump.rs does): params in host memory, three tables out to host memory.
  * Any output pointer may be NULL.  Synchronous. */

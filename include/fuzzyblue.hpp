@@ -51,6 +51,7 @@ public:
     Builder(const Builder&) = delete;
     Builder& operator=(const Builder&) = delete;
     void set_kernels(int kernels) { check(fb_builder_set_kernels(h_, kernels)); }
+    void set_exportable(bool on) { check(fb_builder_set_exportable(h_, on ? 1 : 0)); }   // Vulkan interop, see fuzzyblue.h
     FbBuilder* handle() const { return h_; }
 private:
     FbBuilder* h_ = nullptr;
@@ -87,6 +88,8 @@ public:
         check(fb_atmosphere_read_irradiance(a_, v.data(), v.size() * 4, stream));
         return v;
     }
+    // Vulkan interop: a descriptor of the block holding the three tables (the caller owns it) and where they sit
+    int export_fd(FbExportLayout* layout = nullptr) const { int fd = -1; check(fb_atmosphere_export_fd(a_, &fd, layout)); return fd; }
     const FbAtmosphere* handle() const { return a_; }
 private:
     std::shared_ptr<Builder> builder_;

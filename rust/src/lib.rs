@@ -34,6 +34,10 @@ pub mod ffi {
     pub struct FbDrawParams { pub inverse_viewproj: [[f32; 4]; 4], pub camera_position: [f32; 3], pub _pad: u32, pub sun_direction: [f32; 3] }
     #[repr(C)] #[derive(Copy, Clone, Default)] pub struct FbExtent2D { pub width: u32, pub height: u32 }
     #[repr(C)] #[derive(Copy, Clone, Default)] pub struct FbExtent3D { pub width: u32, pub height: u32, pub depth: u32 }
+    #[repr(C)] #[derive(Copy, Clone, Default)]
+    pub struct FbExportLayout { pub allocation_bytes: usize, pub scattering_offset: usize, pub scattering_bytes: usize,
+                                pub transmittance_offset: usize, pub transmittance_bytes: usize,
+                                pub irradiance_offset: usize, pub irradiance_bytes: usize }
     pub enum FbBuilder {} pub enum FbPending {} pub enum FbAtmosphere {} pub enum FbRenderer {}
     extern "C" {
         pub fn fb_last_error() -> *const c_char;
@@ -48,6 +52,9 @@ pub mod ffi {
         pub fn fb_atmosphere_scattering(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent3D) -> c_int;
         pub fn fb_atmosphere_irradiance(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent2D) -> c_int;
         pub fn fb_atmosphere_destroy(a: *mut FbAtmosphere);
+        // Vulkan interop: the kept block as OPAQUE_FD-importable device memory
+        pub fn fb_builder_set_exportable(b: *mut FbBuilder, on: c_int) -> c_int;
+        pub fn fb_atmosphere_export_fd(a: *const FbAtmosphere, fd: *mut c_int, layout: *mut FbExportLayout) -> c_int;
         pub fn fb_renderer_create(b: *mut FbBuilder, out: *mut *mut FbRenderer) -> c_int;
         pub fn fb_renderer_destroy(r: *mut FbRenderer);
         pub fn fb_renderer_draw(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, depth: *const f32,

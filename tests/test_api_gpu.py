@@ -97,3 +97,37 @@ def test_non_multiple_of_workgroup_dims_are_fully_written():
         assert np.max(np.abs(Ef - ref.irradiance) / np.maximum(ref.irradiance, 1e-30)) <= 1e-3
         e = np.abs(Sf.astype(np.float64) - ref.scattering) / np.maximum(np.abs(ref.scattering), 2.0 ** -14)
         assert (e > 1e-3).mean() <= 2e-3 and e.max() <= 2e-2, (d, e.max())
+
+
+def test_exported_allocation_carries_the_tables():
+    """Vulkan interop: the kept block as an fd-exportable allocation.  With CUDA standing in as the
+    importer (no Vulkan loader in this image): export, import the descriptor afresh, map it, and the three tables read
+    through the import equal the tables read through the Atmosphere."""
+    import os
+    b = fb.Builder(0)
+    b.set_exportable(True)
+    p = fb.Parameters(scattering_r_size=8, scattering_mu_size=32, scattering_mu_s_size=8, scattering_nu_size=2)
+    pend = fb.Atmosphere.build(b, None, p)
+    sync()
+    atm = pend.assert_ready()
+    fd, lay = atm.export_fd()
+    try:
+        assert fd >= 0 and lay.allocation_bytes >= lay.irradiance_offset + lay.irradiance_bytes
+        T, S, E = atm.read_transmittance(), atm.read_scattering(), atm.read_irradiance()
+        assert lay.scattering_bytes == S.nbytes and lay.transmittance_bytes == T.nbytes and lay.irradiance_bytes == E.nbytes
+        S2 = api.external_memory_read(0, fd, lay.allocation_bytes, lay.scattering_offset, S.shape, np.float16)
+        T2 = api.external_memory_read(0, fd, lay.allocation_bytes, lay.transmittance_offset, T.shape, np.float32)
+        E2 = api.external_memory_read(0, fd, lay.allocation_bytes, lay.irradiance_offset, E.shape, np.float32)
+        assert np.array_equal(S, S2) and np.array_equal(T, T2) and np.array_equal(E, E2)
+        assert float(S.astype(np.float32).max()) > 0 and float(T.max()) > 0
+    finally:
+        os.close(fd)
+    atm.close()
+    # the same builder, not exportable: an export request is an error, not a silent copy
+    b.set_exportable(False)
+    pend = fb.Atmosphere.build(b, None, p)
+    sync()
+    atm = pend.assert_ready()
+    with pytest.raises(fb.FuzzyblueError):
+        atm.export_fd()
+    atm.close()
