@@ -108,6 +108,7 @@ ABI = {
     "fb_atmosphere_build": (c_int, [c_void_p, _P(FbParams), c_uint32, c_void_p, _P(c_void_p)]),
     "fb_atmosphere_allocate": (c_int, [c_void_p, _P(FbParams), c_uint32, _P(c_void_p)]),
     "fb_pending_resubmit": (c_int, [c_void_p, c_void_p]),
+    "fb_pending_set_readback": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "fb_pending_launch_count": (c_int, [c_void_p]),
     "fb_pending_run_stage": (c_int, [c_void_p, c_int, c_uint32, c_uint32, c_uint32, c_void_p]),
     "fb_pending_image": (c_int, [c_void_p, c_int, _P(c_void_p), _P(c_size_t)]),
@@ -469,6 +470,11 @@ class PendingAtmosphere:
     def resubmit(self, stream=None):
         """Replay the recorded command stream (what benches/precompute.rs:138-148 times)."""
         _check(_lib().fb_pending_resubmit(self._h, _stream(stream)))
+
+    def set_readback(self, transmittance=None, scattering=None, irradiance=None):
+        """Record the read-back of the finished tables into the command stream: later `resubmit` calls also copy
+        them to these host buffers (addresses of pinned memory, or None), overlapped with the last kernels."""
+        _check(_lib().fb_pending_set_readback(self._h, c_void_p(transmittance), c_void_p(scattering), c_void_p(irradiance)))
 
     def launch_count(self) -> int:
         return _lib().fb_pending_launch_count(self._h)

@@ -7,7 +7,10 @@
 #include <cuda.h>           // driver-API TYPES only (virtual memory management); entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -304,7 +307,11 @@ struct FbAtmosphere {
     float4* transmittance;
     float4* irradiance;
     uint2* scattering;
+    // identity of the table CONTENTS for a renderer's derived copy: `serial` is unique per atmosphere, `version` counts
+    // the submissions that (re)write the tables through the owning PendingAtmosphere
+    uint64_t serial, version;
 };
+static std::atomic<uint64_t> g_atmosphere_serial{1};
 
 struct FbPending {
     FbBuilder* builder;
@@ -319,14 +326,37 @@ struct FbPending {
     int launches;
     cudaStream_t side;       // indirect_irradiance overlaps the density main kernel here (FAST family)
     cudaEvent_t ev_fork, ev_join;
+    // fb_pending_set_readback: host destinations recorded into the command stream.  The last multiple-scattering
+    // pass runs as RB_SLABS r-slabs on streams of descending priority, each followed by the copy of its slab of
+    // `scattering`, so the 8 MiB read-back hides behind the remaining slabs' kernels.
+    void *rb_T, *rb_S, *rb_E;
+    cudaStream_t rb_stream[4];
+    cudaEvent_t rb_ev;
 };
+constexpr int RB_SLABS = 4;
+static int rb_slabs() {      // FUZZYBLUE_B200_RB_SLABS=1..4 overrides the slab count (tuning experiments)
+    static const int n = [] {
+        const char* e = std::getenv("FUZZYBLUE_B200_RB_SLABS");
+        const int v = e ? std::atoi(e) : RB_SLABS;
+        return v < 1 ? 1 : (v > RB_SLABS ? RB_SLABS : v);
+    }();
+    return n;
+}
 
 struct FbRenderer {
     int device;
     int kernels;
     void* sweep_draws;           // device copy of a sweep's draw parameters + per-view constants
     uint32_t sweep_capacity;
+    // the FAST path's expanded copy of one atmosphere's scattering table (fb_render.cu: Tex3X), rebuilt when a draw
+    // names other table contents; draws on other streams wait for the rebuild through `expanded_ready`
+    void* expanded;
+    size_t expanded_bytes;
+    uint64_t expanded_serial, expanded_version;
+    cudaEvent_t expanded_ready;
+    bool no_expand;              // FUZZYBLUE_B200_RENDER_FP16_TABLE set at creation: always tap the fp16 table (A/B tests)
 };
+constexpr size_t EXPANDED_MAX_BYTES = (size_t)256 << 20;
 
 struct DeviceGuard {
     int prev;
@@ -523,6 +553,8 @@ static void free_pending_temps(FbPending* p) {
     if (p->side) { cudaStreamDestroy(p->side); p->side = nullptr; }
     if (p->ev_fork) { cudaEventDestroy(p->ev_fork); p->ev_fork = nullptr; }
     if (p->ev_join) { cudaEventDestroy(p->ev_join); p->ev_join = nullptr; }
+    for (cudaStream_t& q : p->rb_stream) if (q) { cudaStreamDestroy(q); q = nullptr; }
+    if (p->rb_ev) { cudaEventDestroy(p->rb_ev); p->rb_ev = nullptr; }
 }
 
 void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
@@ -562,7 +594,12 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     p->graph = nullptr;
     p->launches = 0;
     p->side = nullptr; p->ev_fork = nullptr; p->ev_join = nullptr;
+    p->rb_T = p->rb_S = p->rb_E = nullptr;
+    for (cudaStream_t& q : p->rb_stream) q = nullptr;
+    p->rb_ev = nullptr;
     a->device = b->device;
+    a->serial = g_atmosphere_serial.fetch_add(1);
+    a->version = 0;
     a->kernels = b->kernels;
     a->P = *params;
     a->transmittance = nullptr; a->irradiance = nullptr; a->scattering = nullptr;
@@ -655,24 +692,56 @@ static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order
 // The recorded command stream, src/precompute.rs:1671-2048.  Stream order replaces the pipeline
 // barriers; the parameter block travels as a kernel argument instead of vkCmdUpdateBuffer.
 static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
+    if (p->inner) ++p->inner->version;
     LaunchCtx c = make_ctx(p, s);
     const int R = p->P.scattering_r_size;
     int st;
-#define STAGE(stage, ord) if ((st = run_stage(p, c, stage, ord, 0, R, launches)) != FB_OK) return st
-    STAGE(FB_STAGE_TRANSMITTANCE, 0);          // :1726-1745
-    STAGE(FB_STAGE_DIRECT_IRRADIANCE, 0);      // :1760-1779  -> delta_irradiance
-    STAGE(FB_STAGE_SINGLE_SCATTERING, 0);      // :1781-1800
-    STAGE(FB_STAGE_CLEAR_IRRADIANCE, 0);       // :1802-1831  direct irradiance is not accumulated
-    const bool overlap = p->builder->kernels == FB_KERNELS_FAST && p->order >= 2;
-    if (overlap && !p->side) {
+    const bool fastk = p->builder->kernels == FB_KERNELS_FAST;
+    const bool overlap = fastk && p->order >= 2;
+    const bool rb = p->rb_T || p->rb_S || p->rb_E;
+    if ((overlap || rb) && !p->side) {
         FB_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
         FB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
         FB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     }
+    if (rb && !p->rb_ev) {
+        int least = 0, greatest = 0;
+        FB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));      // numerically lower = more urgent
+        for (int i = 0; i < RB_SLABS; ++i)
+            FB_CUDA(cudaStreamCreateWithPriority(&p->rb_stream[i], cudaStreamNonBlocking, std::min(greatest + i, least)));
+        FB_CUDA(cudaEventCreateWithFlags(&p->rb_ev, cudaEventDisableTiming));
+    }
+    bool side_used = false;
+    // a finished table leaves for host memory on the side stream while the main stream carries on
+    auto copy_out = [&](cudaStream_t after, void* host, const void* dev, size_t bytes) -> int {
+        if (!host) return FB_OK;
+        if (after != p->side) {
+            FB_CUDA(cudaEventRecord(p->rb_ev, after));
+            FB_CUDA(cudaStreamWaitEvent(p->side, p->rb_ev, 0));
+        }
+        FB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, p->side));
+        side_used = true;
+        return FB_OK;
+    };
+    const size_t bT = image_bytes(p->P, FB_IMAGE_TRANSMITTANCE), bE = image_bytes(p->P, FB_IMAGE_IRRADIANCE),
+                 bS = image_bytes(p->P, FB_IMAGE_SCATTERING);
+#define STAGE(stage, ord) if ((st = run_stage(p, c, stage, ord, 0, R, launches)) != FB_OK) return st
+#define COPY_OUT(after, host, dev, bytes) if ((st = copy_out(after, host, dev, bytes)) != FB_OK) return st
+    STAGE(FB_STAGE_TRANSMITTANCE, 0);          // :1726-1745
+    COPY_OUT(s, p->rb_T, p->img.transmittance, bT);
+    STAGE(FB_STAGE_DIRECT_IRRADIANCE, 0);      // :1760-1779  -> delta_irradiance
+    STAGE(FB_STAGE_SINGLE_SCATTERING, 0);      // :1781-1800
+    STAGE(FB_STAGE_CLEAR_IRRADIANCE, 0);       // :1802-1831  direct irradiance is not accumulated
+    if (p->order < 2) {
+        COPY_OUT(s, p->rb_S, p->img.scattering, bS);
+        COPY_OUT(s, p->rb_E, p->img.irradiance, bE);
+    }
     for (uint32_t order = 2; order <= p->order; ++order) {   // :1853
+        const bool last = order == p->order;
         if (!overlap) {
             STAGE(FB_STAGE_SCATTERING_DENSITY, order);           // :1878-1904, push constant `order`
             STAGE(FB_STAGE_INDIRECT_IRRADIANCE, order - 1);      // :1927-1953, push constant `order - 1`
+            if (last) COPY_OUT(s, p->rb_E, p->img.irradiance, bE);
         } else {
             // K4 reads delta_irradiance (row 0) only in its preparation kernel, K5 overwrites that image and reads
             // nothing K4 writes: K5 runs on a side stream next to K4's main kernel and joins before K6 (which
@@ -681,15 +750,55 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
             if (e != cudaSuccess) return cuda_fail(e, "scattering_density launch");
             if (launches) *launches += fast::launches_per_stage(c.P, FB_STAGE_SCATTERING_DENSITY, R);
             FB_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+            side_used = true;
             LaunchCtx cs = c;
             cs.stream = p->side;
             if ((st = run_stage(p, cs, FB_STAGE_INDIRECT_IRRADIANCE, order - 1, 0, R, launches)) != FB_OK) return st;
             FB_CUDA(cudaEventRecord(p->ev_join, p->side));
             FB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+            if (last) COPY_OUT(p->side, p->rb_E, p->img.irradiance, bE);   // after the join point: K6 does not wait for it
         }
-        STAGE(FB_STAGE_MULTIPLE_SCATTERING, 0);              // :1979-1998
+        const int nsl = (last && p->rb_S && R % rb_slabs() == 0) ? rb_slabs() : 1;
+        if (nsl == 1) {
+            STAGE(FB_STAGE_MULTIPLE_SCATTERING, 0);              // :1979-1998
+            if (last) COPY_OUT(s, p->rb_S, p->img.scattering, bS);
+        } else {
+            // K6 is r-local in what it writes (multiple_scattering.comp:77-92): the last pass runs as r-slabs on
+            // streams of descending priority (the block scheduler drains them in that order, later slabs fill the
+            // tail of earlier ones), each followed by the read-back of its slab of `scattering`.
+            FB_CUDA(cudaEventRecord(p->rb_ev, s));
+            const size_t slab_b = bS / nsl;
+            for (int i = 0; i < nsl; ++i) {
+                cudaStream_t q = p->rb_stream[i];
+                FB_CUDA(cudaStreamWaitEvent(q, p->rb_ev, 0));
+                LaunchCtx cq = c;
+                cq.stream = q;
+                if ((st = run_stage(p, cq, FB_STAGE_MULTIPLE_SCATTERING, 0, i * (R / nsl), (i + 1) * (R / nsl), launches)) != FB_OK)
+                    return st;
+                FB_CUDA(cudaMemcpyAsync(static_cast<char*>(p->rb_S) + i * slab_b,
+                                        reinterpret_cast<const char*>(p->img.scattering) + i * slab_b, slab_b,
+                                        cudaMemcpyDeviceToHost, q));
+            }
+            for (int i = 0; i < nsl; ++i) {
+                FB_CUDA(cudaEventRecord(p->ev_fork, p->rb_stream[i]));
+                FB_CUDA(cudaStreamWaitEvent(s, p->ev_fork, 0));
+            }
+        }
     }
 #undef STAGE
+#undef COPY_OUT
+    if (rb && side_used) {                     // the copies on the side stream are part of the command stream
+        FB_CUDA(cudaEventRecord(p->ev_join, p->side));
+        FB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+    }
+    return FB_OK;
+}
+
+int fb_pending_set_readback(FbPending* p, void* host_transmittance, void* host_scattering, void* host_irradiance) {
+    if (!p || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_set_readback: NULL / already taken");
+    DeviceGuard g(p->builder->device);
+    p->rb_T = host_transmittance; p->rb_S = host_scattering; p->rb_E = host_irradiance;
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }   // re-recorded by the next resubmit
     return FB_OK;
 }
 
@@ -723,6 +832,7 @@ int fb_pending_resubmit(FbPending* p, void* stream) {
         if (e != cudaSuccess) { p->graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
         p->launches = launches;
     }
+    ++p->inner->version;
     FB_CUDA(cudaGraphLaunch(p->graph, (cudaStream_t)stream));
     return FB_OK;
 }
@@ -736,6 +846,7 @@ int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_beg
     DeviceGuard g(p->builder->device);
     LaunchCtx c = make_ctx(p, (cudaStream_t)stream);
     int n = 0;
+    if (p->inner) ++p->inner->version;
     const int st = run_stage(p, c, stage, order, (int)r_begin, (int)r_end, &n);
     p->launches += n;   // stage-driven pendings accumulate; build / resubmit overwrite with the per-submit count
     return st;
@@ -751,6 +862,7 @@ int fb_pending_upload(FbPending* p, int image, const void* host, size_t bytes, v
     if (!p || !host || image < 0 || image >= FB_IMAGE_COUNT) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_upload");
     if (bytes != image_bytes(p->P, image)) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_upload: size mismatch");
     DeviceGuard g(p->builder->device);
+    if (p->inner) ++p->inner->version;
     FB_CUDA(cudaMemcpyAsync(image_ptr(p, image), host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return FB_OK;
 }
@@ -831,12 +943,12 @@ int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, void* T,
     cudaStream_t s;
     FB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     FbPending* pend = nullptr;
-    int st = fb_atmosphere_build(b, p, order, s, &pend);
+    int st = fb_atmosphere_allocate(b, p, order, &pend);
     if (st == FB_OK) {
-        const FbAtmosphere* a = pend->inner;
-        if (T && st == FB_OK) st = fb_atmosphere_read_transmittance(a, T, image_bytes(a->P, FB_IMAGE_TRANSMITTANCE), s);
-        if (S && st == FB_OK) st = fb_atmosphere_read_scattering(a, S, image_bytes(a->P, FB_IMAGE_SCATTERING), s);
-        if (E && st == FB_OK) st = fb_atmosphere_read_irradiance(a, E, image_bytes(a->P, FB_IMAGE_IRRADIANCE), s);
+        // the read-backs ride in the command stream, each table leaving as soon as its last writer has run
+        pend->rb_T = T; pend->rb_S = S; pend->rb_E = E;
+        int launches = 0;
+        st = enqueue_all(pend, s, &launches);
         cudaError_t e = cudaStreamSynchronize(s);
         if (st == FB_OK && e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize");
         fb_pending_destroy(pend);
@@ -895,6 +1007,8 @@ int fb_renderer_create(FbBuilder* b, FbRenderer** out) {
     r->kernels = b->kernels;
     r->sweep_draws = nullptr;
     r->sweep_capacity = 0;
+    r->expanded = nullptr; r->expanded_bytes = 0; r->expanded_serial = 0; r->expanded_version = 0; r->expanded_ready = nullptr;
+    r->no_expand = std::getenv("FUZZYBLUE_B200_RENDER_FP16_TABLE") != nullptr;
     *out = r;
     return FB_OK;
 }
@@ -902,6 +1016,8 @@ void fb_renderer_destroy(FbRenderer* r) {
     if (!r) return;
     DeviceGuard g(r->device);
     cudaFree(r->sweep_draws);
+    cudaFree(r->expanded);
+    if (r->expanded_ready) cudaEventDestroy(r->expanded_ready);
     delete r;
 }
 
@@ -918,7 +1034,35 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
         FB_CUDA(cudaMalloc(&r->sweep_draws, (size_t)views * render_view_record_bytes()));
         r->sweep_capacity = views;
     }
-    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, d, views > 1 ? r->sweep_draws : nullptr, views, depth,
+    // FAST path: keep a (value, delta) fp32 expansion of this atmosphere's scattering table (bit-identical look-ups with
+    // half the instructions per tap).  Tables another API can write behind our back (exportable blocks) and tables whose
+    // expansion would not stay cache-resident anyway use the fp16 table directly.
+    const void* expanded = nullptr;
+    const size_t xb = render_expanded_bytes(a->P);
+    const uint64_t texels = xb / 32;
+    if (r->kernels != FB_KERNELS_REFERENCE && !r->no_expand && !a->vmm && xb <= EXPANDED_MAX_BYTES && texels < (1ull << 31) &&
+        (uint64_t)w * h * views >= texels) {                // tiny draws: the expansion would cost more than it saves
+        if (r->expanded_bytes < xb) {
+            cudaFree(r->expanded);
+            r->expanded = nullptr; r->expanded_bytes = 0; r->expanded_serial = 0;
+            FB_CUDA(cudaMalloc(&r->expanded, xb));
+            r->expanded_bytes = xb;
+        }
+        if (!r->expanded_ready) FB_CUDA(cudaEventCreateWithFlags(&r->expanded_ready, cudaEventDisableTiming));
+        if (r->expanded_serial != a->serial || r->expanded_version != a->version) {
+            // earlier draws (any stream) may still read the old contents: they were ordered before `expanded_ready`'s
+            // last record only on their own streams, so drain them before overwriting
+            if (r->expanded_serial) FB_CUDA(cudaDeviceSynchronize());
+            cudaError_t ee = render_expand_scattering(a->P, a->scattering, r->expanded, (cudaStream_t)stream);
+            if (ee != cudaSuccess) return cuda_fail(ee, "render_expand_scattering launch");
+            FB_CUDA(cudaEventRecord(r->expanded_ready, (cudaStream_t)stream));
+            r->expanded_serial = a->serial; r->expanded_version = a->version;
+        } else {
+            FB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, r->expanded_ready, 0));
+        }
+        expanded = r->expanded;
+    }
+    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, expanded, d, views > 1 ? r->sweep_draws : nullptr, views, depth,
                                (float4*)color, (float4*)transm, (float4*)blend, w, h, r->kernels, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_sky launch");
     return FB_OK;

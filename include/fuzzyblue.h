@@ -165,6 +165,14 @@ FB_API int fb_atmosphere_allocate(FbBuilder* b, const FbParams* p, uint32_t orde
  * re-submitting the pre-recorded command buffer, which is what benches/precompute.rs:138-148
  * times.  The stream is replayed from a CUDA graph instantiated on first use. */
 FB_API int fb_pending_resubmit(FbPending* p, void* stream);
+/* Make the read-back part of the recorded command stream (what examples/dump.rs:175-193 does with
+ * vkCmdCopyImageToBuffer after the precompute): every later fb_pending_resubmit also copies the finished tables,
+ * tightly packed, to these host buffers (pinned memory for an asynchronous copy; NULL = leave that table on the
+ * device).  Each table leaves as soon as its last writer has run: transmittance after the first kernel, irradiance
+ * after the last indirect_irradiance pass, and the last multiple_scattering pass runs in r-slabs whose slices of
+ * `scattering` are copied while the remaining slabs compute.  The buffers must stay valid until the stream has
+ * finished; results on the device are unchanged. */
+FB_API int fb_pending_set_readback(FbPending* p, void* host_transmittance, void* host_scattering, void* host_irradiance);
 /* Number of kernel launches / memset nodes of the last build / resubmit; for a pending driven stage by stage
  * (fb_atmosphere_allocate + fb_pending_run_stage) the running total since allocation. */
 FB_API int fb_pending_launch_count(const FbPending* p);

@@ -112,6 +112,10 @@ public:
         return Atmosphere(builder_, a, true);
     }
     void resubmit(void* stream) { check(fb_pending_resubmit(p_, stream)); }   // benches/precompute.rs:138-148
+    // later resubmits also copy the finished tables to these (pinned) host buffers, overlapped with the last kernels
+    void set_readback(void* transmittance, void* scattering, void* irradiance) {
+        check(fb_pending_set_readback(p_, transmittance, scattering, irradiance));
+    }
     FbPending* handle() const { return p_; }
 private:
     std::shared_ptr<Builder> builder_;

@@ -45,6 +45,7 @@ pub mod ffi {
         pub fn fb_builder_destroy(b: *mut FbBuilder);
         pub fn fb_atmosphere_build(b: *mut FbBuilder, p: *const FbParams, order: u32, stream: *mut c_void, out: *mut *mut FbPending) -> c_int;
         pub fn fb_pending_resubmit(p: *mut FbPending, stream: *mut c_void) -> c_int;
+        pub fn fb_pending_set_readback(p: *mut FbPending, t: *mut c_void, s: *mut c_void, e: *mut c_void) -> c_int;
         pub fn fb_pending_atmosphere(p: *mut FbPending, out: *mut *const FbAtmosphere) -> c_int;
         pub fn fb_pending_assert_ready(p: *mut FbPending, check: c_int, out: *mut *mut FbAtmosphere) -> c_int;
         pub fn fb_pending_destroy(p: *mut FbPending);
@@ -176,6 +177,11 @@ impl PendingAtmosphere {
     }
     /// Re-submit the recorded stream (what benches/precompute.rs:138-148 does with its command buffer).
     pub unsafe fn resubmit(&self, stream: *mut c_void) { check(ffi::fb_pending_resubmit(self.raw, stream)) }
+    /// Later `resubmit`s also copy the finished tables to these pinned host buffers (null = keep on the device),
+    /// overlapped with the last kernels of the command stream.
+    pub unsafe fn set_readback(&self, transmittance: *mut c_void, scattering: *mut c_void, irradiance: *mut c_void) {
+        check(ffi::fb_pending_set_readback(self.raw, transmittance, scattering, irradiance))
+    }
 }
 impl Drop for PendingAtmosphere { fn drop(&mut self) { if !self.raw.is_null() { unsafe { ffi::fb_pending_destroy(self.raw) } } } }
 

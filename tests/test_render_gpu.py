@@ -147,6 +147,38 @@ def test_4k_frame_properties(scene):
     assert np.all(transm[ground][:, :3] >= t2[ground][:, :3] - 1e-6)
 
 
+def test_expanded_table_taps_are_bit_identical(scene, monkeypatch):
+    """Draws of at least one pixel per table texel go through the renderer's (value, delta) fp32 expansion of the
+    scattering table; smaller ones, and a renderer created with FUZZYBLUE_B200_RENDER_FP16_TABLE set, tap the fp16
+    table.  Both must produce the same bits, also after the table contents change under the same atmosphere handle."""
+    import torch
+    W2, H2 = 512, 288
+    draws, extra = synthetic.camera_sweep(24, W2, H2)
+    monkeypatch.setenv("FUZZYBLUE_B200_RENDER_FP16_TABLE", "1")
+    plain = fb.Renderer(scene["builder"])
+    monkeypatch.delenv("FUZZYBLUE_B200_RENDER_FP16_TABLE")
+    expd = fb.Renderer(scene["builder"])
+    for k in (2, 9, 13, 17, 22):
+        depth = synthetic.analytic_depth(extra[k][0], extra[k][1], W2, H2)
+        c0, t0 = plain.draw_host(scene["atm"], draws[k], depth)
+        c1, t1 = expd.draw_host(scene["atm"], draws[k], depth)
+        assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32)) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    # another atmosphere through the same renderer: the expansion must follow the table contents
+    pend = fb.Atmosphere.build(scene["builder"], None, fb.Parameters(order=2, **DUMP_DIMS))
+    torch.cuda.synchronize()
+    k = 13
+    depth = synthetic.analytic_depth(extra[k][0], extra[k][1], W2, H2)
+    for order_atm in (pend.atmosphere(), scene["atm"], pend.atmosphere()):
+        c0, t0 = plain.draw_host(order_atm, draws[k], depth)
+        c1, t1 = expd.draw_host(order_atm, draws[k], depth)
+        assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32)) and np.array_equal(t0.view(np.uint32), t1.view(np.uint32))
+    # same handle, new contents: modify the table in place and replay
+    pend.resubmit(None)
+    torch.cuda.synchronize()
+    c2, _ = expd.draw_host(pend.atmosphere(), draws[k], depth)
+    assert np.array_equal(c2.view(np.uint32), c1.view(np.uint32))
+
+
 def test_fast_family_hoisting_is_exact():
     """The FAST kernel evaluates parameter-only and camera-only sub-expressions once on the host; every texture
     coordinate must still be the one the contraction-free kernel derives per pixel, so the two families agree to the
