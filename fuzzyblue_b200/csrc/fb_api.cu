@@ -729,9 +729,23 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
 #define COPY_OUT(after, host, dev, bytes) if ((st = copy_out(after, host, dev, bytes)) != FB_OK) return st
     STAGE(FB_STAGE_TRANSMITTANCE, 0);          // :1726-1745
     COPY_OUT(s, p->rb_T, p->img.transmittance, bT);
-    STAGE(FB_STAGE_DIRECT_IRRADIANCE, 0);      // :1760-1779  -> delta_irradiance
-    STAGE(FB_STAGE_SINGLE_SCATTERING, 0);      // :1781-1800
-    STAGE(FB_STAGE_CLEAR_IRRADIANCE, 0);       // :1802-1831  direct irradiance is not accumulated
+    if (!overlap) {
+        STAGE(FB_STAGE_DIRECT_IRRADIANCE, 0);      // :1760-1779  -> delta_irradiance
+        STAGE(FB_STAGE_SINGLE_SCATTERING, 0);      // :1781-1800
+        STAGE(FB_STAGE_CLEAR_IRRADIANCE, 0);       // :1802-1831  direct irradiance is not accumulated
+    } else {
+        // K2 and the clear touch the two irradiance images only, K3 reads the transmittance table only: the two small
+        // launches run on the side stream next to K3 and join before the order loop
+        FB_CUDA(cudaEventRecord(p->ev_fork, s));
+        FB_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+        LaunchCtx cs = c;
+        cs.stream = p->side;
+        if ((st = run_stage(p, cs, FB_STAGE_DIRECT_IRRADIANCE, 0, 0, R, launches)) != FB_OK) return st;
+        if ((st = run_stage(p, cs, FB_STAGE_CLEAR_IRRADIANCE, 0, 0, R, launches)) != FB_OK) return st;
+        FB_CUDA(cudaEventRecord(p->ev_join, p->side));
+        STAGE(FB_STAGE_SINGLE_SCATTERING, 0);
+        FB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
+    }
     if (p->order < 2) {
         COPY_OUT(s, p->rb_S, p->img.scattering, bS);
         COPY_OUT(s, p->rb_E, p->img.irradiance, bE);
@@ -775,10 +789,12 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
                 cq.stream = q;
                 if ((st = run_stage(p, cq, FB_STAGE_MULTIPLE_SCATTERING, 0, i * (R / nsl), (i + 1) * (R / nsl), launches)) != FB_OK)
                     return st;
+            }
+            // every slab's kernel is enqueued before the first copy: a copy into pageable memory blocks the calling thread
+            for (int i = 0; i < nsl; ++i)
                 FB_CUDA(cudaMemcpyAsync(static_cast<char*>(p->rb_S) + i * slab_b,
                                         reinterpret_cast<const char*>(p->img.scattering) + i * slab_b, slab_b,
-                                        cudaMemcpyDeviceToHost, q));
-            }
+                                        cudaMemcpyDeviceToHost, p->rb_stream[i]));
             for (int i = 0; i < nsl; ++i) {
                 FB_CUDA(cudaEventRecord(p->ev_fork, p->rb_stream[i]));
                 FB_CUDA(cudaStreamWaitEvent(s, p->ev_fork, 0));

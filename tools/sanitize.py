@@ -16,6 +16,14 @@ for d in cases:
 p = fb.Parameters(**cases[0])
 pend = fb.Atmosphere.build(b, None, p); torch.cuda.synchronize()
 pend.resubmit(None); torch.cuda.synchronize()
+# read-backs recorded into the command stream (r-slabs of the last multiple-scattering pass + their copies)
+hT = torch.zeros((p.transmittance_r_size, p.transmittance_mu_size, 4)).pin_memory()
+hE = torch.zeros((p.irradiance_r_size, p.irradiance_mu_s_size, 4)).pin_memory()
+hS = torch.zeros((p.scattering_r_size, p.scattering_mu_size, p.scattering_nu_size * p.scattering_mu_s_size, 4), dtype=torch.float16).pin_memory()
+pend.set_readback(hT.data_ptr(), hS.data_ptr(), hE.data_ptr())
+pend.resubmit(None); torch.cuda.synchronize()
+assert np.array_equal(hS.numpy().view(np.uint16), pend.atmosphere().read_scattering().view(np.uint16))
+pend.set_readback(None, None, None)
 atm = pend.assert_ready()
 r = fb.Renderer(b)
 draws, extra = synthetic.camera_sweep(14, 64, 36)
