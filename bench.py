@@ -91,7 +91,12 @@ def cpu_precompute_ms(stride: int):
     """Estimated full default-dims 4-order precompute on the CPU oracle from a bounded sample: the 2-D stages in full,
     every 3-D stage on every `stride`-th texel (seeded offset), scaled by `stride`."""
     import numpy as np
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core.  libgomp reads
+    # the variable when the oracle library is first loaded.
+    if "oracle.oracle" not in sys.modules:
+        os.environ["OMP_NUM_THREADS"] = str(host_cores())
     from oracle import oracle as O
+    O.set_threads(host_cores())
     p = O.Params()
     n_tex = int(np.prod(p.s_shape[:3]))
     idx = np.arange(stride // 2, n_tex, stride, dtype=np.int64)
@@ -154,8 +159,12 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     total = args.steps + args.warmup
-    # a full default-dims pass costs ~15 s on 16 cores: pick the texel stride that keeps the whole run near two minutes
-    stride = max(1, math.ceil(total * 15.0 / 120.0))
+    # calibrate on a thin sample (every 64th texel), then pick the texel stride that keeps the whole run near 100 s
+    # whatever the core count is
+    t0 = time.perf_counter()
+    cpu_precompute_ms(64)
+    full_s = max((time.perf_counter() - t0) * 64.0, 1.0)          # estimated cost of a pass over every texel
+    stride = max(1, math.ceil(total * full_s / 100.0))
     vals, sample = [], ""
     for i in range(total):
         ms, sample = cpu_precompute_ms(stride)

@@ -1055,7 +1055,7 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
     // expansion would not stay cache-resident anyway use the fp16 table directly.
     const void* expanded = nullptr;
     const size_t xb = render_expanded_bytes(a->P);
-    const uint64_t texels = xb / 32;
+    const uint64_t texels = xb / 32;                        // (value, delta) float4 pairs; the trailing constants slot rounds away
     if (r->kernels != FB_KERNELS_REFERENCE && !r->no_expand && !a->vmm && xb <= EXPANDED_MAX_BYTES && texels < (1ull << 31) &&
         (uint64_t)w * h * views >= texels) {                // tiny draws: the expansion would cost more than it saves
         if (r->expanded_bytes < xb) {
@@ -1069,7 +1069,7 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
             // earlier draws (any stream) may still read the old contents: they were ordered before `expanded_ready`'s
             // last record only on their own streams, so drain them before overwriting
             if (r->expanded_serial) FB_CUDA(cudaDeviceSynchronize());
-            cudaError_t ee = render_expand_scattering(a->P, a->scattering, r->expanded, (cudaStream_t)stream);
+            cudaError_t ee = render_expand_scattering(a->P, a->transmittance, a->scattering, r->expanded, (cudaStream_t)stream);
             if (ee != cudaSuccess) return cuda_fail(ee, "render_expand_scattering launch");
             FB_CUDA(cudaEventRecord(r->expanded_ready, (cudaStream_t)stream));
             r->expanded_serial = a->serial; r->expanded_version = a->version;

@@ -70,7 +70,8 @@ size_t render_view_record_bytes();
 // `expanded` (may be NULL): render_expanded_bytes() of device memory holding render_expand_scattering()'s output for this
 // scattering table — the FAST path's private (value, delta-to-next-x) fp32 form of it.
 size_t render_expanded_bytes(const FbParams& P);
-cudaError_t render_expand_scattering(const FbParams& P, const uint2* scattering, void* expanded, cudaStream_t s);
+cudaError_t render_expand_scattering(const FbParams& P, const float4* transmittance, const uint2* scattering, void* expanded,
+                                     cudaStream_t s);
 cudaError_t render_sky(const FbParams& P, const float4* transmittance, const uint2* scattering, const void* expanded,
                        const FbDrawParams* draws_host, void* view_records_dev, uint32_t views, const float* depth, float4* color, float4* transm,
                        float4* blend_fb, uint32_t w, uint32_t h, int kernels, cudaStream_t s);

@@ -32,6 +32,8 @@
 #include <limits>
 #include <vector>
 
+#include <omp.h>
+
 namespace {
 
 // ---------------------------------------------------------------------------------------
@@ -783,6 +785,9 @@ template <class F> int dispatch(const void* params, int mode, F&& f) {
 extern "C" {
 
 int fbo_params_size(void) { return int(sizeof(RawParams)); }
+// worker threads of the texel loops (launchers such as torchrun export OMP_NUM_THREADS=1 to their children)
+void fbo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int fbo_max_threads(void) { return omp_get_max_threads(); }
 double fbo_round_to_half(double v) { return round_to_half(v); }
 
 int fbo_transmittance(const void* params, int mode, double* T) {

@@ -36,6 +36,12 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def set_threads(n: int) -> int:
+    """Number of OpenMP worker threads of the texel loops (returns the count in effect)."""
+    lib().fbo_set_threads(int(n))
+    return int(lib().fbo_max_threads())
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -46,6 +52,8 @@ def lib():
         i64 = ctypes.POINTER(ctypes.c_int64)
         vp, ci, c64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
         L.fbo_params_size.restype = ci
+        L.fbo_set_threads.argtypes = [ci]
+        L.fbo_max_threads.restype = ci
         L.fbo_round_to_half.restype = ctypes.c_double
         L.fbo_round_to_half.argtypes = [ctypes.c_double]
         L.fbo_transmittance.argtypes = [vp, ci, d]
