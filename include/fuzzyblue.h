@@ -244,7 +244,13 @@ FB_API void fb_external_semaphore_destroy(FbExternalSemaphore* s);
 FB_API int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, void* transmittance_f32,
                               void* scattering_f16, void* irradiance_f32);
 
-/* Renderer::new, src/render.rs:34-40 (render pass / subpass / frame count have no CUDA meaning). */
+/* Renderer::new, src/render.rs:34-40 (render pass / subpass / frame count have no CUDA meaning).
+ * A renderer keeps device scratch of its own: the draw blocks of a sweep and, for draws of at least one pixel per
+ * scattering texel, an fp32 (value, delta) expansion of the scattering table it last drew from (32 bytes per texel,
+ * up to 256 MiB; bit-identical look-ups at half the instructions).  The expansion is re-derived, after a device-wide
+ * synchronisation, when a draw names other table contents, so alternate between atmospheres with one renderer each.
+ * As with the reference's Renderer (descriptor sets per frame, render.rs:34-40), draws through one renderer are
+ * externally synchronised by the caller. */
 FB_API int fb_renderer_create(FbBuilder* b, FbRenderer** out);
 FB_API void fb_renderer_destroy(FbRenderer* r);
 /* Renderer::draw, src/render.rs:209-236 + shaders/render_sky.frag:24-35, one thread per pixel.

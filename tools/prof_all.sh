@@ -10,6 +10,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 
 python bench.py --workload hires --steps 3 --warmup 3 --no-cpu-baseline > $O/bench_hires.json 2> $O/bench_hires.err
 python bench.py --workload batch --steps 1 --warmup 3 --no-cpu-baseline > $O/bench_batch.json 2> $O/bench_batch.err
 python tools/time_stages.py 20 > $O/stage_times.txt 2>&1
+python tools/time_e2e.py 30 > $O/e2e.txt 2>&1
+( timeout 300 compute-sanitizer --tool memcheck python tools/sanitize.py ) > $O/memcheck.log 2>&1
 # every launch of one step with its device time (cold-cache, serialised)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 16 -c 16 --csv --log-file $O/launches_step.csv python tools/prof_step.py 2 > /dev/null 2>&1
 # full-set capture: single scattering, density order 2, multiple scattering, density order >= 3 (stage-driven pass of prof_step)
