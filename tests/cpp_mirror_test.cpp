@@ -23,6 +23,17 @@ int main() {
     cudaStreamCreate(&stream);
     PendingAtmosphere pending = build(builder, stream, params);
     cudaStreamSynchronize(stream);
+    // the read-back recorded into the command stream (examples/dump.rs:175-193 records its copies the same way)
+    const size_t nT = (size_t)params.raw.transmittance_mu_size * params.raw.transmittance_r_size * 4;
+    const size_t nS = (size_t)params.raw.scattering_nu_size * params.raw.scattering_mu_s_size * params.raw.scattering_mu_size *
+                      params.raw.scattering_r_size * 4;
+    float* hT = nullptr;
+    unsigned short* hS = nullptr;
+    if (cudaMallocHost((void**)&hT, nT * sizeof(float)) != cudaSuccess || cudaMallocHost((void**)&hS, nS * 2) != cudaSuccess) return 7;
+    for (size_t i = 0; i < nS; ++i) hS[i] = 0xffffu;
+    pending.set_readback(hT, hS, nullptr);
+    pending.resubmit(stream);
+    cudaStreamSynchronize(stream);
     Atmosphere atm = std::move(pending).assert_ready();
     auto T = atm.read_transmittance(stream);
     auto E = atm.read_irradiance(stream);
@@ -30,6 +41,9 @@ int main() {
     // KAT (iii): r = top, mu = 1 -> T = 1; alpha = 1
     size_t last_row = (size_t)(atm.transmittance_extent().height - 1) * atm.transmittance_extent().width * 4;
     if (T[last_row] != 1.0f || T[last_row + 3] != 1.0f) return 4;
+    for (size_t i = 0; i < nT; ++i) if (hT[i] != T[i]) return 8;
+    for (size_t i = 3; i < nS; i += 4) if (hS[i] == 0xffffu) return 9;     // every texel of every r-slab arrived
+    cudaFreeHost(hT); cudaFreeHost(hS);
     double sum = 0;
     for (float v : E) { if (!std::isfinite(v)) return 5; sum += v; }
     if (!(sum > 0)) return 6;
