@@ -313,7 +313,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                         "achieved_gbs": 3 * 8 * 32 * 128 * 256 / (dens_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_file) else "fallback"}}
 
-    render = render_leg(args, builder, pending, stream, dev) if world == 1 else None
+    render = render_leg(args, builder, pending, stream, dev, fma_tflops, sfu_gops) if world == 1 else None
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -462,7 +462,31 @@ def run_batch(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
-def render_leg(args, builder, pending, stream, dev):
+# SURVEY.md §8(a) row a24, as-written tallies per pixel: fp32 flops (fma = 2) and SFU-class operations
+RENDER_TALLY = {"geometry": (430, 39), "sky": (290, 29)}
+
+
+def render_roofline(px: int, geometry_px: int, total_ms: float, fma_tflops, sfu_gops):
+    """FP32 / SFU roofline of the sky evaluation over the sweep: the as-written tally of render_sky.h:111-191
+    (a sky pixel skips the far-point look-up) against the peaks fb_builder_measure_peaks measured on
+    this device.  `frac` = max(F / peak_F, S / peak_S) / measured time.  The FAST kernel hoists per-view invariants, so
+    the fraction is an as-written-equivalent rate, not a pipe utilisation (ncu: profiles/r1_render_full_raw.csv)."""
+    if not fma_tflops or not sfu_gops or total_ms <= 0:
+        return None
+    sky_px = px - geometry_px
+    flops = geometry_px * RENDER_TALLY["geometry"][0] + sky_px * RENDER_TALLY["sky"][0]
+    sfu = geometry_px * RENDER_TALLY["geometry"][1] + sky_px * RENDER_TALLY["sky"][1]
+    t = total_ms * 1e-3
+    f_frac = flops / t / 1e12 / fma_tflops
+    s_frac = sfu / t / 1e9 / sfu_gops
+    return {"kernel": "k_render_sky", "bound": "sfu" if s_frac >= f_frac else "fp32", "frac": max(f_frac, s_frac),
+            "fp32": {"achieved_tflops": flops / t / 1e12, "peak_tflops": fma_tflops, "frac": f_frac},
+            "sfu": {"achieved_gops": sfu / t / 1e9, "peak_gops": sfu_gops, "frac": s_frac},
+            "geometry_pixel_share": geometry_px / px if px else None,
+            "tally": "as written, per pixel: geometry 430 flop + 39 SFU ops, sky 290 + 29 (SURVEY.md §8a a24)"}
+
+
+def render_leg(args, builder, pending, stream, dev, fma_tflops=None, sfu_gops=None):
     """Second half of BASELINE.json's metric: sky evaluation at 3840x2160 over a 256-view camera sweep
     (config[4]), in chunks of 8 views (depth + two RGBA32F outputs per chunk = 2.4 GB >> L2)."""
     import numpy as np
@@ -496,7 +520,7 @@ def render_leg(args, builder, pending, stream, dev):
         z = t * (fwd[:, None, None] * d).sum(0)
         return torch.where(hit, 0.1 / z.clamp_min(1e-9), torch.zeros_like(z)).float()
 
-    total_ms, px, n_launch = 0.0, 0, 0
+    total_ms, px, n_launch, geometry_px = 0.0, 0, 0, 0
     for c0 in range(0, VIEWS, CHUNK):
         n = min(CHUNK, VIEWS - c0)
         for j in range(n):
@@ -512,6 +536,7 @@ def render_leg(args, builder, pending, stream, dev):
         total_ms += e0.elapsed_time(e1)
         px += n * W * H
         n_launch += 1
+        geometry_px += int((depth[:n] > 0).sum().item())      # finite-depth pixels take the two-look-up path
     mpx = px / (total_ms * 1e-3) / 1e6
     # end to end for one 4K frame: depth from pinned host memory in, both RGBA32F outputs back to pinned host memory
     hd = depth[0].cpu().pin_memory()
@@ -534,9 +559,11 @@ def render_leg(args, builder, pending, stream, dev):
         frame()
         times.append(time.perf_counter() - t0)
     e2e_s = sorted(times)[len(times) // 2]      # PCIe-bound (33 MB in, 265 MB out per frame): median of 9 frames
+    roofline = render_roofline(px, geometry_px, total_ms, fma_tflops, sfu_gops)
     return {"metric": "sky evaluation Mpixel/s at 3840x2160", "value": mpx, "unit": "Mpixel/s", "views": VIEWS,
             "ms_per_frame": total_ms / VIEWS, "gpu_launches": n_launch, "inputs": "depth + outputs per 8-view chunk 2.4 GB > L2",
             "hbm": {"bytes_per_pixel": 36, "achieved_gbs": 36 * px / (total_ms * 1e-3) / 1e9},
+            "roofline": roofline,
             "e2e": {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4,
                     "d2h_bytes_per_step": W * H * 32}}
 
