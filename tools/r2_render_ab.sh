@@ -1,6 +1,9 @@
 #!/bin/bash
 # A/B of the staged sky-evaluation variants against the product build, one GPU pass (run under gpurun AFTER building
-# the variants here: `tools/build_render_variant.sh magicfloor "-DFB_RENDER_MAGIC_FLOOR=1"`; the .so files travel).
+# the variants here; the .so files travel):
+#   tools/build_render_variant.sh magicfloor "-DFB_RENDER_MAGIC_FLOOR=1"
+#   tools/build_render_variant.sh skysplit "-DFB_RENDER_SKY_SPLIT=1"
+#   tools/build_render_variant.sh skysplit_magic "-DFB_RENDER_SKY_SPLIT=1 -DFB_RENDER_MAGIC_FLOOR=1"
 # For each variant: tools/render_ab.py writes one SHA-256 per output of a 41-view sweep and the device time of the 4K
 # frames; a variant is adopted only if its hash file is identical to the product build's and it is faster.
 set -u
