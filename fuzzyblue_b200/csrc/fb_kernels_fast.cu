@@ -1035,8 +1035,16 @@ struct MultiNode {       // per trapezoid node, block-uniform; three 16-byte wor
 #ifndef FB_MS_CU
 #define FB_MS_CU 4       // unroll of the per-texel node loop
 #endif
+// -DFB_MS_TPT2=1 (staged for round 2, not the default build): default-width rows run as 128-thread CTAs with two texels
+// per thread and 8 CTAs per SM.  The node records are CTA-uniform, but a broadcast LDS still costs one data-pipe cycle
+// per 4 bytes per lane (tools/lds_bench.cu): per warp and node, 5 wavefronts in the sample loop and 8 in the staging
+// loop next to ~10 for the two slab taps (tools/analyze_ms_banks.py).  Two texels per thread halve the record loads per
+// sample; the per-texel arithmetic and its order are unchanged, so the results are bit-identical.
+#ifndef FB_MS_TPT2
+#define FB_MS_TPT2 0
+#endif
 template <int TPT, int NTMAX>   // TPT texels per thread: the CTA covers the whole (nu, mu_s) row, W <= TPT * blockDim.x
-__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : 1) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
+__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 128 ? 8 : 1)) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
                                                               uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
     constexpr int CU = FB_MS_CU;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1258,6 +1266,12 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
     const size_t smem = sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4);
     if (smem > 200 * 1024) return ref::multiple_scattering(c, r0, r1);
+#if FB_MS_TPT2
+    if (W == 256) {                               // 128 threads x 2 texels, half the slab so that 8 CTAs fit an SM
+        const int ch2 = 1536 / W;
+        return multiple_launch<2, 128>(c, 128, ch2, sizeof(MultiNode) * NS + (size_t)ch2 * W * sizeof(float4), r0, r1);
+    }
+#endif
     if (nt <= 256) return multiple_launch<1, 256>(c, nt, CH, smem, r0, r1);
     if (tpt == 1) return multiple_launch<1, 1024>(c, nt, CH, smem, r0, r1);
     if (tpt == 2) return multiple_launch<2, 1024>(c, nt, CH, smem, r0, r1);
