@@ -1018,9 +1018,21 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     return cudaGetLastError();
 }
 
-struct MultiNode {       // per trapezoid node, block-uniform; three 16-byte words so each is one (broadcast) LDS.128
+// -DFB_MS_DIET=1 (staged for round 2, not the default build): the staging half of a node record shrinks from two
+// broadcast LDS.128 (four weights, four row offsets) to one (first row offset, the two row steps, the two cell
+// fractions); the weights are rebuilt per thread by the same fp32 operations on the same operands (1 - f, four
+// products), the offsets by integer adds, so the staged entries are bit-identical.  A broadcast load costs a
+// data-pipe cycle per 4 bytes per lane like any other, and that pipe is what binds this kernel.
+#ifndef FB_MS_DIET
+#define FB_MS_DIET 0
+#endif
+struct MultiNode {       // per trapezoid node, block-uniform; 16-byte words so each is one (broadcast) LDS.128
+#if FB_MS_DIET
+    uint4 st;            // offset of row (y0, z0), (y1 - y0) * W | ((z1 - z0) * mu_size * W in .y), fy bits (.z), fz bits (.w)
+#else
     float4 w;            // bilinear weights of the (mu, r) cell of GetScattering(r_i, mu_i, ., ., hits): (y0z0, y1z0, y0z1, y1z1)
     uint4 off;           // texel offsets of those four rows in the density table
+#endif
     float4 t;            // GetTransmittance(r, mu, d_i) * dx * trapezoid weight (rgb), node distance d_i
     float inv_r, pad0, pad1, pad2;   // 1 / r_i
 };
@@ -1132,10 +1144,18 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
             F fy, fz;
             tex_axis(uvwz[2], P.scattering_mu_size, y0, y1, fy);
             tex_axis(uvwz[3], P.scattering_r_size, z0, z1, fz);
+#if FB_MS_DIET
+            // the two row steps fit 16 bits each only for small tables: keep them as full words, (dy, dz) in .y's halves
+            // would not; .y carries dy * W, the z step is rebuilt from the flag in its top bit
+            nodes[i].st = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W),
+                                     (unsigned)((y1 - y0) * W) | ((unsigned)(z1 - z0) << 31),
+                                     __float_as_uint(fy.v), __float_as_uint(fz.v));
+#else
             const float gy = 1.f - fy.v, gz = 1.f - fz.v;
             nodes[i].w = make_float4(gy * gz, fy.v * gz, gy * fz.v, fy.v * fz.v);
             nodes[i].off = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W), (unsigned)((z0 * P.scattering_mu_size + y1) * W),
                                       (unsigned)((z1 * P.scattering_mu_size + y0) * W), (unsigned)((z1 * P.scattering_mu_size + y1) * W));
+#endif
             nodes[i].inv_r = (F(1.f) / r_i).v; nodes[i].pad0 = nodes[i].pad1 = nodes[i].pad2 = 0.f;
         }
     }
@@ -1160,16 +1180,33 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
                 // left the loop waiting on L2 latency every iteration).
                 for (int e0 = 0; e0 < cn; e0 += FB_MS_U) {
                     uint2 raw[FB_MS_U][4];
+#if FB_MS_DIET
+                    float2 frac[FB_MS_U];
+                    const uint32_t zstep = (uint32_t)P.scattering_mu_size * (uint32_t)W;
+#endif
 #pragma unroll
                     for (int u = 0; u < FB_MS_U; ++u) {
+#if FB_MS_DIET
+                        const uint4 st = nodes[c0 + min(e0 + u, cn - 1)].st;
+                        const uint32_t dy = st.y & 0x7fffffffu, dz = (st.y >> 31) ? zstep : 0u;
+                        const uint4 o = make_uint4(st.x, st.x + dy, st.x + dz, st.x + dz + dy);
+                        frac[u] = make_float2(__uint_as_float(st.z), __uint_as_float(st.w));
+#else
                         const uint4 o = nodes[c0 + min(e0 + u, cn - 1)].off;   // 32-bit texel indices: one IMAD.WIDE per address
+#endif
                         raw[u][0] = __ldg(dens + (o.x + xi)); raw[u][1] = __ldg(dens + (o.y + xi));
                         raw[u][2] = __ldg(dens + (o.z + xi)); raw[u][3] = __ldg(dens + (o.w + xi));
                     }
 #pragma unroll
                     for (int u = 0; u < FB_MS_U; ++u) {
                         if (e0 + u < cn) {
+#if FB_MS_DIET
+                            // frac[u] belongs to node min(e0 + u, cn - 1) == e0 + u here
+                            const float gy = 1.f - frac[u].x, gz = 1.f - frac[u].y;
+                            const float4 w = make_float4(gy * gz, frac[u].x * gz, gy * frac[u].y, frac[u].x * frac[u].y);
+#else
                             const float4 w = nodes[c0 + e0 + u].w;
+#endif
                             const float4 a00 = unpack_half4(raw[u][0]), a10 = unpack_half4(raw[u][1]);
                             const float4 a01 = unpack_half4(raw[u][2]), a11 = unpack_half4(raw[u][3]);
                             float4 v;

@@ -2,6 +2,8 @@
 # A/B of the staged precompute variants against the product build, one GPU pass (run under gpurun AFTER building the
 # variants here; the .so files travel):
 #   tools/build_variant.sh ms_tpt2 "-DFB_MS_TPT2=1"
+#   tools/build_variant.sh ms_diet "-DFB_MS_DIET=1"
+#   tools/build_variant.sh ms_tpt2_diet "-DFB_MS_DIET=1 -DFB_MS_TPT2=1"
 # tools/precompute_ab.py writes one SHA-256 per table for three dims and the per-stage device times; a bit-identical
 # variant is adopted only if its hash file equals the product build's and its stage is faster.
 set -u
