@@ -56,7 +56,21 @@ def wavefronts(idx):
         out += worst
     return out
 
-tot = {"current": 0, "ideal": 0, "pad1": 0, "pairs32B": 0}
+def wavefronts_w(idx, lanes, groups):
+    """LDS of narrower words: `lanes` lanes per wavefront (16 for LDS.64, 32 for LDS.32), `groups` bank groups."""
+    q = idx.reshape(idx.shape[:-1] + (32 // lanes, lanes))
+    out = np.zeros(idx.shape[:-1], int)
+    for qq in range(32 // lanes):
+        g = q[..., qq, :]
+        worst = np.zeros(idx.shape[:-1], int)
+        for b in range(groups):
+            vals = np.sort(np.where((g % groups) == b, g, -1), axis=-1)
+            distinct = (np.diff(vals, axis=-1) != 0).sum(-1) + 1 - (vals[..., 0] == -1)
+            worst = np.maximum(worst, distinct)
+        out += worst
+    return out
+
+tot = {"current": 0, "ideal": 0, "pad1": 0, "pairs32B": 0, "planes_rg_b": 0, "planes_r_g_b": 0}
 n_loads = 0
 i_nodes = np.arange(51)
 for z in range(0, R):
@@ -83,8 +97,12 @@ for z in range(0, R):
             tot["pad1"] += wavefronts(basep).sum() + wavefronts(basep + 1).sum()
             # (value, next value) pairs in one 32-byte entry: two LDS.128 at 2 * idx and 2 * idx + 1
             tot["pairs32B"] += wavefronts(2 * base).sum() + wavefronts(2 * base + 1).sum()
+            # (r, g) float2 plane + b float plane: LDS.64 + LDS.32 per tap, 3 words per lane instead of 4
+            tot["planes_rg_b"] += (wavefronts_w(base, 16, 16).sum() + wavefronts_w(base + 1, 16, 16).sum()
+                                   + wavefronts_w(base, 32, 32).sum() + wavefronts_w(base + 1, 32, 32).sum())
+            tot["planes_r_g_b"] += 3 * (wavefronts_w(base, 32, 32).sum() + wavefronts_w(base + 1, 32, 32).sum())
             tot["ideal"] += 2 * 4 * 51
             n_loads += 2 * 51
 print("LDS.128 per sampled rows:", n_loads, " (two taps per sample, one nu slice)")
 for kname, v in tot.items():
-    print("%-9s wavefronts per LDS.128: %.2f" % (kname, v / n_loads))
+    print("%-11s wavefronts per tap: %.2f" % (kname, v / n_loads))
