@@ -1167,6 +1167,118 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
     // u * MS - 0.5 with u = 0.5/MS + xx * (1 - 1/MS)  ==  xx * (MS - 1)
     const float msm1 = (float)(MS - 1);
     const float tmax = __int_as_float(__float_as_int(msm1) - 1);
+#if FB_MS_TPT2
+    // Node loop outside, the thread's TPT texels inside: one (broadcast) record load serves all of them.  Per texel the
+    // staged entries and the order of the accumulation over the nodes are those of the loop in the #else branch.
+    bool actk[TPT];
+    bool act_any = false, two_any = false;
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        const int xk = threadIdx.x + k * blockDim.x;
+        actk[k] = xk < W && leader[k] == xk;
+        act_any |= actk[k];
+        two_any |= actk[k] && two[k];
+    }
+    const bool warp_act = __any_sync(0xffffffffu, act_any);      // warp-uniform
+    const bool warp_two = __any_sync(0xffffffffu, two_any);
+    for (int c0 = 0; c0 < NS; c0 += CH) {
+        const int cn = min(CH, NS - c0);
+        __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
+        constexpr int U2 = 2;                     // nodes in flight: U2 * TPT * 4 row loads per thread
+        for (int e0 = 0; e0 < cn; e0 += U2) {
+            uint2 raw[U2][TPT][4];
+#if FB_MS_DIET
+            float2 frac[U2];
+            const uint32_t zstep = (uint32_t)P.scattering_mu_size * (uint32_t)W;
+#endif
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+#if FB_MS_DIET
+                const uint4 st = nodes[c0 + min(e0 + u, cn - 1)].st;
+                const uint32_t dy = st.y & 0x7fffffffu, dz = (st.y >> 31) ? zstep : 0u;
+                const uint4 o = make_uint4(st.x, st.x + dy, st.x + dz, st.x + dz + dy);
+                frac[u] = make_float2(__uint_as_float(st.z), __uint_as_float(st.w));
+#else
+                const uint4 o = nodes[c0 + min(e0 + u, cn - 1)].off;
+#endif
+#pragma unroll
+                for (int k = 0; k < TPT; ++k) {
+                    const uint32_t xi = (uint32_t)min((int)(threadIdx.x + k * blockDim.x), W - 1);
+                    raw[u][k][0] = __ldg(dens + (o.x + xi)); raw[u][k][1] = __ldg(dens + (o.y + xi));
+                    raw[u][k][2] = __ldg(dens + (o.z + xi)); raw[u][k][3] = __ldg(dens + (o.w + xi));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                if (e0 + u < cn) {
+#if FB_MS_DIET
+                    const float gy = 1.f - frac[u].x, gz = 1.f - frac[u].y;
+                    const float4 w = make_float4(gy * gz, frac[u].x * gz, gy * frac[u].y, frac[u].x * frac[u].y);
+#else
+                    const float4 w = nodes[c0 + e0 + u].w;
+#endif
+#pragma unroll
+                    for (int k = 0; k < TPT; ++k) {
+                        const int x = threadIdx.x + k * blockDim.x;
+                        if (x < W) {
+                            const float4 a00 = unpack_half4(raw[u][k][0]), a10 = unpack_half4(raw[u][k][1]);
+                            const float4 a01 = unpack_half4(raw[u][k][2]), a11 = unpack_half4(raw[u][k][3]);
+                            float4 v;
+                            v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
+                            v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
+                            v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
+                            v.w = 0.f;
+                            slab[(e0 + u) * W + x] = v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (warp_act) {
+#define FB_MS_BODY(k, TWO)                                                                                                  \
+            if (actk[k]) {                                                                                                  \
+                const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf[k], rmus[k]) * inv_r, -1.f), 1.f);       /* :38 */           \
+                const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));                                 \
+                const float aa = (dd - dmin) * inv_span;                                                                    \
+                const float xx = fmaxf(fmaf(aa, minvA, 1.f), 0.f) * rcp_fast(1.f + aa);                                     \
+                const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);                                                         \
+                const float tm = __fadd_rd(t, 8388608.f);                                                                   \
+                const int j = __float_as_int(tm) - 0x4B000000;                                                              \
+                const float fx = t - (tm - 8388608.f);                                                                      \
+                const float4* s = slab + e * W + j;                                                                         \
+                const float4 p00 = s[kx0[k]], p01 = s[kx0[k] + 1];                                                          \
+                float vr = fmaf(fx, p01.x - p00.x, p00.x), vg = fmaf(fx, p01.y - p00.y, p00.y), vb = fmaf(fx, p01.z - p00.z, p00.z); \
+                if (TWO) {                                                                                                  \
+                    const float4 p10 = s[kx1[k]], p11 = s[kx1[k] + 1];                                                      \
+                    const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z); \
+                    vr = fmaf(ln[k], v1r - vr, vr); vg = fmaf(ln[k], v1g - vg, vg); vb = fmaf(ln[k], v1b - vb, vb);         \
+                }                                                                                                           \
+                ar[k] = fmaf(vr, nt.x, ar[k]);                                                                              \
+                ag[k] = fmaf(vg, nt.y, ag[k]);                                                                              \
+                ab[k] = fmaf(vb, nt.z, ab[k]);                                                                              \
+            }
+            if (warp_two) {
+#pragma unroll 2
+                for (int e = 0; e < cn; ++e) {
+                    const float4 nt = nodes[c0 + e].t;
+                    const float inv_r = nodes[c0 + e].inv_r;
+#pragma unroll
+                    for (int k = 0; k < TPT; ++k) FB_MS_BODY(k, two[k])
+                }
+            } else {
+#pragma unroll 2
+                for (int e = 0; e < cn; ++e) {
+                    const float4 nt = nodes[c0 + e].t;
+                    const float inv_r = nodes[c0 + e].inv_r;
+#pragma unroll
+                    for (int k = 0; k < TPT; ++k) FB_MS_BODY(k, false)
+                }
+            }
+#undef FB_MS_BODY
+        }
+    }
+#else
     for (int c0 = 0; c0 < NS; c0 += CH) {
         const int cn = min(CH, NS - c0);
         __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
@@ -1263,6 +1375,7 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
             }
         }
     }
+#endif
     __syncthreads();                              // last chunk consumed: the slab now carries the leaders' results
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
