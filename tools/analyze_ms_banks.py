@@ -10,7 +10,7 @@ bottom, top, mu_s_min = 6360.0, 6420.0, -0.207912
 R, MU, MS, NU = 32, 128, 32, 8
 W = NU * MS
 H = np.sqrt(top * top - bottom * bottom)
-stride = int(sys.argv[1]) if len(sys.argv) > 1 else 7
+stride = int(sys.argv[1]) if len(sys.argv) > 1 and __name__ == "__main__" else 7
 
 def row_geometry(z, y):
     rho = H * z / (R - 1)
@@ -70,39 +70,40 @@ def wavefronts_w(idx, lanes, groups):
         out += worst
     return out
 
-tot = {"current": 0, "ideal": 0, "pad1": 0, "pairs32B": 0, "planes_rg_b": 0, "planes_r_g_b": 0}
-n_loads = 0
-i_nodes = np.arange(51)
-for z in range(0, R):
-    for y in range(z % stride, MU, stride):
-        r, mu, L = row_geometry(z, y)
-        d_i = i_nodes * (L / 50.0)
-        r_i = np.clip(np.sqrt(d_i * d_i + 2 * r * mu * d_i + r * r), bottom, top)
-        for k in range(NU):
-            nu_k = 2.0 * k / (NU - 1) - 1.0
-            s = np.sqrt(np.maximum((1 - mu * mu) * (1 - mu_s_tex * mu_s_tex), 0))
-            nu = np.clip(nu_k, mu * mu_s_tex - s, mu * mu_s_tex + s)                       # [32]
-            tcx = (nu + 1) / 2 * (NU - 1)
-            tx = np.clip(np.floor(tcx + 1e-6).astype(int), 0, NU - 1)
-            mus_i = np.clip((r * mu_s_tex[None, :] + d_i[:, None] * nu[None, :]) / r_i[:, None], -1, 1)   # [51, 32]
-            dd = -bottom * mus_i + np.sqrt(bottom * bottom * (mus_i * mus_i - 1) + top * top)
-            aa = (dd - dmin_s) / (dmax_s - dmin_s)
-            xx = np.maximum(1 - aa / A, 0) / (1 + aa)
-            t = np.clip(xx * (MS - 1), 0, MS - 1 - 1e-6)
-            j = np.floor(t).astype(int)                                                 # [51, 32]
-            e = (i_nodes % 12)[:, None]
-            base = e * W + j + (tx * MS)[None, :]
-            tot["current"] += wavefronts(base).sum() + wavefronts(base + 1).sum()
-            basep = e * (W + 1) + j + (tx * MS)[None, :]
-            tot["pad1"] += wavefronts(basep).sum() + wavefronts(basep + 1).sum()
-            # (value, next value) pairs in one 32-byte entry: two LDS.128 at 2 * idx and 2 * idx + 1
-            tot["pairs32B"] += wavefronts(2 * base).sum() + wavefronts(2 * base + 1).sum()
-            # (r, g) float2 plane + b float plane: LDS.64 + LDS.32 per tap, 3 words per lane instead of 4
-            tot["planes_rg_b"] += (wavefronts_w(base, 16, 16).sum() + wavefronts_w(base + 1, 16, 16).sum()
-                                   + wavefronts_w(base, 32, 32).sum() + wavefronts_w(base + 1, 32, 32).sum())
-            tot["planes_r_g_b"] += 3 * (wavefronts_w(base, 32, 32).sum() + wavefronts_w(base + 1, 32, 32).sum())
-            tot["ideal"] += 2 * 4 * 51
-            n_loads += 2 * 51
-print("LDS.128 per sampled rows:", n_loads, " (two taps per sample, one nu slice)")
-for kname, v in tot.items():
-    print("%-11s wavefronts per tap: %.2f" % (kname, v / n_loads))
+if __name__ == "__main__":
+    tot = {"current": 0, "ideal": 0, "pad1": 0, "pairs32B": 0, "planes_rg_b": 0, "planes_r_g_b": 0}
+    n_loads = 0
+    i_nodes = np.arange(51)
+    for z in range(0, R):
+        for y in range(z % stride, MU, stride):
+            r, mu, L = row_geometry(z, y)
+            d_i = i_nodes * (L / 50.0)
+            r_i = np.clip(np.sqrt(d_i * d_i + 2 * r * mu * d_i + r * r), bottom, top)
+            for k in range(NU):
+                nu_k = 2.0 * k / (NU - 1) - 1.0
+                s = np.sqrt(np.maximum((1 - mu * mu) * (1 - mu_s_tex * mu_s_tex), 0))
+                nu = np.clip(nu_k, mu * mu_s_tex - s, mu * mu_s_tex + s)                       # [32]
+                tcx = (nu + 1) / 2 * (NU - 1)
+                tx = np.clip(np.floor(tcx + 1e-6).astype(int), 0, NU - 1)
+                mus_i = np.clip((r * mu_s_tex[None, :] + d_i[:, None] * nu[None, :]) / r_i[:, None], -1, 1)   # [51, 32]
+                dd = -bottom * mus_i + np.sqrt(bottom * bottom * (mus_i * mus_i - 1) + top * top)
+                aa = (dd - dmin_s) / (dmax_s - dmin_s)
+                xx = np.maximum(1 - aa / A, 0) / (1 + aa)
+                t = np.clip(xx * (MS - 1), 0, MS - 1 - 1e-6)
+                j = np.floor(t).astype(int)                                                 # [51, 32]
+                e = (i_nodes % 12)[:, None]
+                base = e * W + j + (tx * MS)[None, :]
+                tot["current"] += wavefronts(base).sum() + wavefronts(base + 1).sum()
+                basep = e * (W + 1) + j + (tx * MS)[None, :]
+                tot["pad1"] += wavefronts(basep).sum() + wavefronts(basep + 1).sum()
+                # (value, next value) pairs in one 32-byte entry: two LDS.128 at 2 * idx and 2 * idx + 1
+                tot["pairs32B"] += wavefronts(2 * base).sum() + wavefronts(2 * base + 1).sum()
+                # (r, g) float2 plane + b float plane: LDS.64 + LDS.32 per tap, 3 words per lane instead of 4
+                tot["planes_rg_b"] += (wavefronts_w(base, 16, 16).sum() + wavefronts_w(base + 1, 16, 16).sum()
+                                       + wavefronts_w(base, 32, 32).sum() + wavefronts_w(base + 1, 32, 32).sum())
+                tot["planes_r_g_b"] += 3 * (wavefronts_w(base, 32, 32).sum() + wavefronts_w(base + 1, 32, 32).sum())
+                tot["ideal"] += 2 * 4 * 51
+                n_loads += 2 * 51
+    print("LDS.128 per sampled rows:", n_loads, " (two taps per sample, one nu slice)")
+    for kname, v in tot.items():
+        print("%-11s wavefronts per tap: %.2f" % (kname, v / n_loads))
