@@ -999,6 +999,150 @@ __global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant
     S[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, mie.x.v);
 }
 
+// -DFB_SS_TPT2=1 (staged for round 2, not the default build): the STAGED body above with two texels per thread
+// (128-thread CTAs, 8 per SM, half-size slab) and the node loop outside the texel loop, so that one broadcast load of
+// a node record (10 words in the sample pass, 6 in the staging pass -- as much data-pipe time as the two slab taps)
+// serves two texels / two staged columns.  Per texel the arithmetic and the order of the sum over the nodes are
+// unchanged: bit-identical tables.
+#ifndef FB_SS_TPT2
+#define FB_SS_TPT2 0
+#endif
+#if FB_SS_TPT2
+__global__ void __launch_bounds__(128, 8) k_single_scattering_t2(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
+                                                                  uint2* __restrict__ dM, uint2* __restrict__ S, int r0, int CH) {
+    constexpr int TPT = 2, NT = 128;
+    __shared__ SingleNode nodes[NS];
+    __shared__ float s_dx;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* slab = reinterpret_cast<float4*>(smem_raw);
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    const int xb = blockIdx.x * (TPT * NT), y = blockIdx.y, z = r0 + blockIdx.z;
+    A<F> a(P);
+    F r, mu;
+    bool hits;
+    float r_mu_s[TPT], nuf[TPT];
+    bool active[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        const int x = xb + threadIdx.x + k * NT;
+        F mu_s, nu;
+        a.TexelToRMuMuSNu((unsigned)min(x, W - 1), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);   // r, mu, hits: functions of (y, z)
+        r_mu_s[k] = (r * mu_s).v; nuf[k] = nu.v; active[k] = x < W;
+    }
+    const F H = f_sqrt(a.top() * a.top() - a.bottom() * a.bottom());
+    {   // node records: threads i and 64 + i share node i (as in k_single_scattering)
+        const int j = threadIdx.x, i = j & 63;
+        if (i < NS) {
+            const bool partA = j < 64, partB = j >= 64;
+            const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);
+            const F d = F((float)i) * dx;
+            if (partA) {
+                const V tr = a.Transmittance(T, r, mu, d, hits);                            // :19-21
+                nodes[i].t.x = tr.x.v; nodes[i].t.y = tr.y.v; nodes[i].t.z = tr.z.v;
+                if (i == 0) s_dx = dx.v;
+            }
+            if (partB) {
+                const F r_d = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));  // single_scattering.comp:16
+                nodes[i].g0 = make_float4(d.v, (F(1.f) / r_d).v, r_d.v, (r_d * r_d).v);
+                const F rho = A<F>::SafeSqrt(r_d * r_d - a.bottom() * a.bottom());          // transmittance.h:14
+                const F d_min = a.top() - r_d, d_max = rho + H;
+                const F v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size);           // transmittance.h:21-23
+                int y0, y1;
+                F fy;
+                tex_axis(v, P.transmittance_r_size, y0, y1, fy);
+                nodes[i].row0 = y0 * P.transmittance_mu_size; nodes[i].row1 = y1 * P.transmittance_mu_size;
+                const F sin_h = a.bottom() / r_d;                                           // transmittance.h:67-73
+                const F cos_h = -f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)));
+                const F al = F(P.sun_angular_radius);
+                const F e0 = -sin_h * al, e1 = sin_h * al;
+                nodes[i].g1 = make_float4(d_min.v, (F(1.f) / (d_max - d_min)).v, (cos_h + e0).v, (F(1.f) / (e1 - e0)).v);
+                nodes[i].t.w = fy.v;
+                const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);
+                nodes[i].rho_r = (A<F>::ProfileDensity(P.rayleigh_density, r_d - a.bottom()) * w).v;   // :24-27
+                nodes[i].rho_m = (A<F>::ProfileDensity(P.mie_density, r_d - a.bottom()) * w).v;
+            }
+        }
+    }
+    const float tt = P.top_radius * P.top_radius;
+    const int TW = P.transmittance_mu_size;
+    const float un = (float)(TW - 1);
+    const float umax = __int_as_float(__float_as_int(un) - 1);
+    float rsr[TPT], rsg[TPT], rsb[TPT], msr[TPT], msg[TPT], msb[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) rsr[k] = rsg[k] = rsb[k] = msr[k] = msg[k] = msb[k] = 0.f;
+    for (int c0 = 0; c0 < NS; c0 += CH) {
+        const int cn = min(CH, NS - c0);
+        __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
+        for (int jb = 0; jb < TW; jb += TPT * NT) {
+            for (int e0 = 0; e0 < cn; e0 += 2) {
+                float4 ra[2][TPT], rb[2][TPT];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {     // 8 row loads in flight per thread
+                    const SingleNode& n = nodes[c0 + min(e0 + u, cn - 1)];
+                    const int row0 = n.row0, row1 = n.row1;
+#pragma unroll
+                    for (int q = 0; q < TPT; ++q) {
+                        const int j = min(jb + (int)threadIdx.x + q * NT, TW - 1);
+                        ra[u][q] = __ldg(T.p + row0 + j); rb[u][q] = __ldg(T.p + row1 + j);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (e0 + u < cn) {
+                        const float4 nt = nodes[c0 + e0 + u].t;
+#pragma unroll
+                        for (int q = 0; q < TPT; ++q) {
+                            const int j = jb + (int)threadIdx.x + q * NT;
+                            if (j < TW)
+                                slab[(e0 + u) * TW + j] = make_float4(fmaf(nt.w, rb[u][q].x - ra[u][q].x, ra[u][q].x) * nt.x,
+                                                                      fmaf(nt.w, rb[u][q].y - ra[u][q].y, ra[u][q].y) * nt.y,
+                                                                      fmaf(nt.w, rb[u][q].z - ra[u][q].z, ra[u][q].z) * nt.z, 0.f);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int e = 0; e < cn; ++e) {
+            const int i = c0 + e;
+            const float4 g0 = nodes[i].g0, g1 = nodes[i].g1;
+            const float rr = nodes[i].rho_r, rm = nodes[i].rho_m;
+#pragma unroll
+            for (int k = 0; k < TPT; ++k) {
+                if (active[k]) {
+                    const float mu_s_d = fminf(fmaxf(fmaf(g0.x, nuf[k], r_mu_s[k]) * g0.y, -1.f), 1.f);   // :17
+                    const float disc = fmaf(g0.w, fmaf(mu_s_d, mu_s_d, -1.f), tt);                        // params.h:105-110
+                    const float dtop = fmaxf(fmaf(-g0.z, mu_s_d, sqrt_fast(fmaxf(disc, 0.f))), 0.f);
+                    const float tu = fminf(fmaxf((dtop - g1.x) * g1.y * un, 0.f), umax);                  // transmittance.h:20-22
+                    const float tm = __fadd_rd(tu, 8388608.f);
+                    const int j = __float_as_int(tm) - 0x4B000000;
+                    const float fx = tu - (tm - 8388608.f);
+                    const float4 p0 = slab[e * TW + j], p1 = slab[e * TW + j + 1];
+                    float sm = fminf(fmaxf((mu_s_d - g1.z) * g1.w, 0.f), 1.f);                            // transmittance.h:71-73
+                    sm = sm * sm * fmaf(-2.f, sm, 3.f);
+                    const float tr_ = fmaf(fx, p1.x - p0.x, p0.x) * sm, tg_ = fmaf(fx, p1.y - p0.y, p0.y) * sm, tb_ = fmaf(fx, p1.z - p0.z, p0.z) * sm;
+                    rsr[k] = fmaf(tr_, rr, rsr[k]); rsg[k] = fmaf(tg_, rr, rsg[k]); rsb[k] = fmaf(tb_, rr, rsb[k]);
+                    msr[k] = fmaf(tr_, rm, msr[k]); msg[k] = fmaf(tg_, rm, msg[k]); msb[k] = fmaf(tb_, rm, msb[k]);
+                }
+            }
+        }
+    }
+    const F dx = F(s_dx);
+#pragma unroll
+    for (int k = 0; k < TPT; ++k) {
+        const int x = xb + threadIdx.x + k * NT;
+        if (x >= W) continue;
+        const V ray = V(F(rsr[k]), F(rsg[k]), F(rsb[k])) * dx * V(P.solar_irradiance) * V(P.rayleigh_scattering);   // :62-64
+        const V mie = V(F(msr[k]), F(msg[k]), F(msb[k])) * dx * V(P.solar_irradiance) * V(P.mie_scattering);
+        const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
+        dR[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, 0.f);
+        dM[o] = pack_half4(mie.x.v, mie.y.v, mie.z.v, 0.f);
+        S[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, mie.x.v);
+    }
+}
+#endif
+
 cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
     const int nt = W >= 256 ? 256 : ((W + 31) / 32) * 32;
@@ -1012,6 +1156,17 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
         k_single_scattering<false><<<g, nt, 0, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, 0);
         return cudaGetLastError();
     }
+#if FB_SS_TPT2
+    if (W % 256 == 0 && TW <= 256) {              // 128 threads x 2 texels, half the slab so that 8 CTAs fit an SM
+        const int ch2 = 1536 / TW < 1 ? 1 : 1536 / TW;
+        const size_t smem2 = (size_t)ch2 * TW * sizeof(float4);
+        cudaError_t e2 = cudaFuncSetAttribute(k_single_scattering_t2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        k_single_scattering_t2<<<dim3(W / 256, c.P.scattering_mu_size, r1 - r0), 128, smem2, c.stream>>>(
+            c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, ch2);
+        return cudaGetLastError();
+    }
+#endif
     cudaError_t e = cudaFuncSetAttribute(k_single_scattering<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_single_scattering<true><<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, CH);
