@@ -133,9 +133,27 @@ static inline size_t density_tab_floats(const FbParams& P) {
 }
 static inline size_t density_grow_floats(const FbParams& P) { return (size_t)P.scattering_r_size * (DL / 2) * P.irradiance_mu_s_size * 6; }
 
+// -DFB_DENSITY_ROWS=1 (staged for round 2, not the default build): what k_density_main's prologue derives per CTA
+// although it depends on the (r, mu) row only -- the exact texel geometry (sx, sy, mu_s) of the row's texels and the
+// 512 phase / extinction weights -- is written once per launch by k_density_rows (same expressions, same operations:
+// bit-identical values) and the main kernel loads it: the prologue is ~15 % of a CTA's life and keeps half of the SM's
+// warps off the data pipe while it runs.  Scratch grows by [R][mu][W + 512] float4 (48 MiB at default dims).
+#ifndef FB_DENSITY_ROWS
+#define FB_DENSITY_ROWS 0
+#endif
+static inline size_t density_base_floats(const FbParams& P) {   // table + ground rows + hit flags, rounded to 16 bytes
+    return (density_tab_floats(P) + density_grow_floats(P) + (size_t)P.scattering_r_size * DL + 3) / 4 * 4;
+}
+static inline size_t density_rows_float4(const FbParams& P) {
+    return (size_t)P.scattering_r_size * P.scattering_mu_size * ((size_t)P.scattering_nu_size * P.scattering_mu_s_size + DL * 32);
+}
 size_t scratch_bytes(const FbParams& P) {
     if (!density_supported(P)) return 0;
+#if FB_DENSITY_ROWS
+    return density_base_floats(P) * sizeof(float) + density_rows_float4(P) * sizeof(float4);
+#else
     return (density_tab_floats(P) + density_grow_floats(P) + (size_t)P.scattering_r_size * DL) * sizeof(float);
+#endif
 }
 
 template <bool ORDER2>
@@ -261,11 +279,63 @@ __device__ __forceinline__ void density_tap(uint32_t addr, float f, float nu1, f
 constexpr int GN_MAXR = 64;
 struct GroundNormals { float2 n[GN_MAXR][DL / 2]; };
 
+#if FB_DENSITY_ROWS
+// one CTA per (r, mu) row: rowsG[row][x] = (sx, sy, mu_s, 0) of texel x, rowsW[row][l * 32 + m] = the weight of sample
+// (theta_l, phi_m); the expressions are those of k_density_main's prologue (scattering_density.comp:28-32, :93-103)
+__global__ void __launch_bounds__(256) k_density_rows(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg,
+                                                      float4* __restrict__ rowsG, float4* __restrict__ rowsW, int r0) {
+    const int tid = threadIdx.x, y = blockIdx.x, z = r0 + blockIdx.y;
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    const size_t row = (size_t)z * P.scattering_mu_size + y;
+    A<F> a(P);
+    F r, mu;
+    for (int x0 = 0; x0 < W; x0 += 256) {
+        const int x = x0 + tid;
+        const bool valid = x < W;
+        F mu_s, nu;
+        bool hu;
+        a.TexelToRMuMuSNu(valid ? (unsigned)x : 0u, (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hu);
+        if (valid) {
+            F ox = f_sqrt(F(1.f) - mu * mu);
+            F sx = ox == F(0.f) ? F(0.f) : (nu - mu * mu_s) / ox;
+            F sy = f_sqrt(f_max(F(1.f) - sx * sx - mu_s * mu_s, F(0.f)));
+            rowsG[row * W + x] = make_float4(sx.v, sy.v, mu_s.v, 0.f);
+        }
+    }
+    {
+        const float ox = f_sqrt(F(1.f) - mu * mu).v, muf = mu.v;
+        const F ray_rho = A<F>::ProfileDensity(P.rayleigh_density, r - a.bottom());
+        const F mie_rho = A<F>::ProfileDensity(P.mie_density, r - a.bottom());
+        const float dd_ = (F(FB_PI_F) / F(16.f) * (F(FB_PI_F) / F(16.f))).v;        // dtheta * dphi
+        const float g = P.mie_phase_function_g;
+        const float kRw = 3.f / (16.f * FB_PI_F), kMw = 3.f / (8.f * FB_PI_F) * (1.f - g * g) / (2.f + g * g);
+        const float g2p1w = 1.f + g * g, m2gw = -2.f * g;
+        const float rr_ = P.rayleigh_scattering[0] * ray_rho.v, rg_ = P.rayleigh_scattering[1] * ray_rho.v,
+                    rb_ = P.rayleigh_scattering[2] * ray_rho.v;
+        const float mr_ = P.mie_scattering[0] * mie_rho.v, mg_ = P.mie_scattering[1] * mie_rho.v, mb_ = P.mie_scattering[2] * mie_rho.v;
+        for (int e = tid; e < DL * 32; e += 256) {
+            const int l = e >> 5, m = e & 31;
+            const float st = tg.st16[l], ct = tg.ct16[l];
+            const float nu2 = fmaf(ox, tg.cp32[m] * st, muf * ct);
+            const float dw = dd_ * st;
+            const float pr = fmaf(nu2 * kRw, nu2, kRw) * dw;
+            const float rs = rsqrt_fast(fmaf(m2gw, nu2, g2p1w));
+            const float pm = fmaf(nu2 * kMw, nu2, kMw) * (rs * rs * rs) * dw;
+            rowsW[row * (DL * 32) + e] = make_float4(fmaf(rr_, pr, mr_ * pm), fmaf(rg_, pr, mg_ * pm), fmaf(rb_, pr, mb_ * pm), 0.f);
+        }
+    }
+}
+#endif
+
 template <bool ORDER2>
 __global__ void __launch_bounds__(256, 2)
 k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float* __restrict__ tabG,
                const float* __restrict__ hitG, const float2* __restrict__ growG, uint2* __restrict__ out, int r0,
-               uint32_t magic_tab, uint32_t magic_row, const __grid_constant__ GroundNormals GN) {
+               uint32_t magic_tab, uint32_t magic_row, const __grid_constant__ GroundNormals GN
+#if FB_DENSITY_ROWS
+               , const float4* __restrict__ rowsG, const float4* __restrict__ rowsW
+#endif
+               ) {
     typedef DensityCfg<ORDER2> C;
     constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
     constexpr bool PAIRED = C::PAIRED;
@@ -294,6 +364,33 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         tma_bulk_g2s(smem_raw, tabG + ((size_t)z * dd.tiles + tile) * DL * TT * ENT, TAB_B, bar);
     }
 
+#if FB_DENSITY_ROWS
+    // ---- row constants written by k_density_rows: texel geometry into geoS, the lane's 48 weights into registers
+    if (tid < TT) {
+        const int nui = tid >> dd.ms_shift, msl = tid & (dd.ms_tile - 1);
+        const int ms = tile * dd.ms_tile + msl;
+        float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (ms < P.scattering_mu_s_size) {
+            g = __ldg(rowsG + ((size_t)z * P.scattering_mu_size + y) * W + (nui * P.scattering_mu_s_size + ms));
+            g.w = __int_as_float(msl * dd.nu * ENT_B);                              // .w: byte offset of the texel's rows
+        }
+        geoS[tid] = g;
+    }
+    float Wr[DL], Wg[DL], Wb[DL];
+    {
+        const float4* wrow = rowsW + ((size_t)z * P.scattering_mu_size + y) * (DL * 32) + lane;
+#pragma unroll
+        for (int l = 0; l < DL; ++l) {
+            const float4 w = __ldg(wrow + l * 32);
+            Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
+        }
+    }
+    uint32_t gmask = 0;                                                        // theta rows that reach the ground (CTA-uniform)
+    for (int l = DL / 2; l < DL; ++l)
+        if (__ldg(hitG + (size_t)z * DL + l) != 0.f) gmask |= 1u << l;
+    (void)WtS;
+    __syncthreads();
+#else
     A<F> a(P);
     // ---- texel geometry, exact (scattering_density.comp:28-32) ------------------------------------------
     // One evaluation per thread: thread t < TT takes texel t of the tile; r and mu (functions of y, z only) come out of
@@ -355,6 +452,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         const float4 w = WtS[l * 32 + lane];
         Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
     }
+#endif
     // ---- work list ------------------------------------------------------------------------------------------
     // Every nu knot outside [mu mu_s - s, mu mu_s + s] is clamped onto the same bound (scattering.h:133-136), so a
     // texel whose (sx, sy, mu_s) equal those of the previous nu slice has bit-identical inputs: it is a FOLLOWER and
@@ -678,6 +776,12 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, hit, c.img.delta_irradiance, grow, r0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+#if FB_DENSITY_ROWS
+    float4* rowsG = reinterpret_cast<float4*>(tab + density_base_floats(P));
+    float4* rowsW = rowsG + (size_t)P.scattering_r_size * P.scattering_mu_size * W;
+    k_density_rows<<<dim3(P.scattering_mu_size, r1 - r0), 256, 0, c.stream>>>(P, c.trig, rowsG, rowsW, r0);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+#endif
     // from here on nothing reads delta_irradiance: indirect_irradiance may run concurrently with the main kernel
     if (after_prep && (e = cudaEventRecord(after_prep, c.stream)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -702,7 +806,11 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
         }
         dim3 gm(d.tiles, P.scattering_mu_size, nz_);
         k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, hit, grow, c.img.scattering_density, zc,
-                                                                      0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u, gn);
+                                                                      0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u, gn
+#if FB_DENSITY_ROWS
+                                                                      , rowsG, rowsW
+#endif
+                                                                      );
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -1586,7 +1694,7 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
 
 int launches_per_stage(const FbParams& P, int stage, int r_count) {
     if (stage != FB_STAGE_SCATTERING_DENSITY || !density_supported(P)) return 1;
-    return 1 + (r_count + GN_MAXR - 1) / GN_MAXR;   // preparation + one main launch per GN_MAXR levels
+    return 1 + FB_DENSITY_ROWS + (r_count + GN_MAXR - 1) / GN_MAXR;   // preparation (+ row constants) + one main launch per GN_MAXR levels
 }
 
 }  // namespace fast

@@ -13,7 +13,7 @@ HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g
 
 CASES = [("fb_render.cu", ["-DFB_RENDER_SKY_SPLIT=1", "-DFB_RENDER_MAGIC_FLOOR=1"]),
          ("fb_render.cu", ["-DFB_RENDER_IEEE_GUARDS=1"]),
-         ("fb_kernels_fast.cu", ["-DFB_MS_DIET=1", "-DFB_MS_TPT2=1", "-DFB_SS_TPT2=1"])]
+         ("fb_kernels_fast.cu", ["-DFB_MS_DIET=1", "-DFB_MS_TPT2=1", "-DFB_SS_TPT2=1", "-DFB_DENSITY_ROWS=1"])]
 
 
 @pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not installed")

@@ -10,4 +10,5 @@ tools/build_variant.sh pre_ms_diet "-DFB_MS_DIET=1" > /dev/null 2>&1 && echo bui
 tools/build_variant.sh pre_ms_tpt2 "-DFB_MS_TPT2=1" > /dev/null 2>&1 && echo built build/variants/pre_ms_tpt2.so
 tools/build_variant.sh pre_ms_tpt2_diet "-DFB_MS_DIET=1 -DFB_MS_TPT2=1" > /dev/null 2>&1 && echo built build/variants/pre_ms_tpt2_diet.so
 tools/build_variant.sh pre_ss_tpt2 "-DFB_SS_TPT2=1" > /dev/null 2>&1 && echo built build/variants/pre_ss_tpt2.so
-tools/build_variant.sh pre_all "-DFB_SS_TPT2=1 -DFB_MS_DIET=1 -DFB_MS_TPT2=1" > /dev/null 2>&1 && echo built build/variants/pre_all.so
+tools/build_variant.sh pre_density_rows "-DFB_DENSITY_ROWS=1" > /dev/null 2>&1 && echo built build/variants/pre_density_rows.so
+tools/build_variant.sh pre_all "-DFB_DENSITY_ROWS=1 -DFB_SS_TPT2=1 -DFB_MS_DIET=1 -DFB_MS_TPT2=1" > /dev/null 2>&1 && echo built build/variants/pre_all.so
