@@ -1431,6 +1431,7 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
     const float msm1 = (float)(MS - 1);
     const float tmax = __int_as_float(__float_as_int(msm1) - 1);
 #if FB_MS_TPT2
+    if constexpr (NTMAX == 128) {                 // the two-texel CTAs of default-width rows only
     // Node loop outside, the thread's TPT texels inside: one (broadcast) record load serves all of them.  Per texel the
     // staged entries and the order of the accumulation over the nodes are those of the loop in the #else branch.
     bool actk[TPT];
@@ -1541,7 +1542,8 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
 #undef FB_MS_BODY
         }
     }
-#else
+    } else {
+#endif
     for (int c0 = 0; c0 < NS; c0 += CH) {
         const int cn = min(CH, NS - c0);
         __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
@@ -1637,6 +1639,8 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
 #undef FB_MS_SAMPLE
             }
         }
+    }
+#if FB_MS_TPT2
     }
 #endif
     __syncthreads();                              // last chunk consumed: the slab now carries the leaders' results
