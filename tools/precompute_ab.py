@@ -21,6 +21,7 @@ IMAGES = [("transmittance", api.IMAGE_TRANSMITTANCE), ("irradiance", api.IMAGE_I
           ("delta_multiple_scattering", api.IMAGE_DELTA_MULTIPLE_SCATTERING)]
 CASES = [("default", dict()),
          ("reduced", dict(scattering_r_size=16, scattering_mu_size=64, scattering_mu_s_size=16, scattering_nu_size=4)),
+         ("wide", dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=64, scattering_nu_size=32)),   # tests/conftest.py WIDE_DIMS: W = 2048, 1024 threads x 2 texels
          ("odd", dict(scattering_r_size=7, scattering_mu_size=22, scattering_mu_s_size=11, scattering_nu_size=3,
                       transmittance_mu_size=100, transmittance_r_size=33, irradiance_mu_s_size=20, irradiance_r_size=9))]
 pend_default = None
