@@ -133,27 +133,9 @@ static inline size_t density_tab_floats(const FbParams& P) {
 }
 static inline size_t density_grow_floats(const FbParams& P) { return (size_t)P.scattering_r_size * (DL / 2) * P.irradiance_mu_s_size * 6; }
 
-// -DFB_DENSITY_ROWS=1 (staged for round 2, not the default build): what k_density_main's prologue derives per CTA
-// although it depends on the (r, mu) row only -- the exact texel geometry (sx, sy, mu_s) of the row's texels and the
-// 512 phase / extinction weights -- is written once per launch by k_density_rows (same expressions, same operations:
-// bit-identical values) and the main kernel loads it: the prologue is ~15 % of a CTA's life and keeps half of the SM's
-// warps off the data pipe while it runs.  Scratch grows by [R][mu][W + 512] float4 (48 MiB at default dims).
-#ifndef FB_DENSITY_ROWS
-#define FB_DENSITY_ROWS 0
-#endif
-static inline size_t density_base_floats(const FbParams& P) {   // table + ground rows + hit flags, rounded to 16 bytes
-    return (density_tab_floats(P) + density_grow_floats(P) + (size_t)P.scattering_r_size * DL + 3) / 4 * 4;
-}
-static inline size_t density_rows_float4(const FbParams& P) {
-    return (size_t)P.scattering_r_size * P.scattering_mu_size * ((size_t)P.scattering_nu_size * P.scattering_mu_s_size + DL * 32);
-}
 size_t scratch_bytes(const FbParams& P) {
     if (!density_supported(P)) return 0;
-#if FB_DENSITY_ROWS
-    return density_base_floats(P) * sizeof(float) + density_rows_float4(P) * sizeof(float4);
-#else
     return (density_tab_floats(P) + density_grow_floats(P) + (size_t)P.scattering_r_size * DL) * sizeof(float);
-#endif
 }
 
 template <bool ORDER2>
@@ -279,62 +261,12 @@ __device__ __forceinline__ void density_tap(uint32_t addr, float f, float nu1, f
 constexpr int GN_MAXR = 64;
 struct GroundNormals { float2 n[GN_MAXR][DL / 2]; };
 
-#if FB_DENSITY_ROWS
-// one CTA per (r, mu) row: rowsG[row][x] = (sx, sy, mu_s, 0) of texel x, rowsW[row][l * 32 + m] = the weight of sample
-// (theta_l, phi_m); the expressions are those of k_density_main's prologue (scattering_density.comp:28-32, :93-103)
-__global__ void __launch_bounds__(256) k_density_rows(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg,
-                                                      float4* __restrict__ rowsG, float4* __restrict__ rowsW, int r0) {
-    const int tid = threadIdx.x, y = blockIdx.x, z = r0 + blockIdx.y;
-    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    const size_t row = (size_t)z * P.scattering_mu_size + y;
-    A<F> a(P);
-    F r, mu;
-    for (int x0 = 0; x0 < W; x0 += 256) {
-        const int x = x0 + tid;
-        const bool valid = x < W;
-        F mu_s, nu;
-        bool hu;
-        a.TexelToRMuMuSNu(valid ? (unsigned)x : 0u, (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hu);
-        if (valid) {
-            F ox = f_sqrt(F(1.f) - mu * mu);
-            F sx = ox == F(0.f) ? F(0.f) : (nu - mu * mu_s) / ox;
-            F sy = f_sqrt(f_max(F(1.f) - sx * sx - mu_s * mu_s, F(0.f)));
-            rowsG[row * W + x] = make_float4(sx.v, sy.v, mu_s.v, 0.f);
-        }
-    }
-    {
-        const float ox = f_sqrt(F(1.f) - mu * mu).v, muf = mu.v;
-        const F ray_rho = A<F>::ProfileDensity(P.rayleigh_density, r - a.bottom());
-        const F mie_rho = A<F>::ProfileDensity(P.mie_density, r - a.bottom());
-        const float dd_ = (F(FB_PI_F) / F(16.f) * (F(FB_PI_F) / F(16.f))).v;        // dtheta * dphi
-        const float g = P.mie_phase_function_g;
-        const float kRw = 3.f / (16.f * FB_PI_F), kMw = 3.f / (8.f * FB_PI_F) * (1.f - g * g) / (2.f + g * g);
-        const float g2p1w = 1.f + g * g, m2gw = -2.f * g;
-        const float rr_ = P.rayleigh_scattering[0] * ray_rho.v, rg_ = P.rayleigh_scattering[1] * ray_rho.v,
-                    rb_ = P.rayleigh_scattering[2] * ray_rho.v;
-        const float mr_ = P.mie_scattering[0] * mie_rho.v, mg_ = P.mie_scattering[1] * mie_rho.v, mb_ = P.mie_scattering[2] * mie_rho.v;
-        for (int e = tid; e < DL * 32; e += 256) {
-            const int l = e >> 5, m = e & 31;
-            const float st = tg.st16[l], ct = tg.ct16[l];
-            const float nu2 = fmaf(ox, tg.cp32[m] * st, muf * ct);
-            const float dw = dd_ * st;
-            const float pr = fmaf(nu2 * kRw, nu2, kRw) * dw;
-            const float rs = rsqrt_fast(fmaf(m2gw, nu2, g2p1w));
-            const float pm = fmaf(nu2 * kMw, nu2, kMw) * (rs * rs * rs) * dw;
-            rowsW[row * (DL * 32) + e] = make_float4(fmaf(rr_, pr, mr_ * pm), fmaf(rg_, pr, mg_ * pm), fmaf(rb_, pr, mb_ * pm), 0.f);
-        }
-    }
-}
-#endif
 
 template <bool ORDER2>
 __global__ void __launch_bounds__(256, 2)
 k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float* __restrict__ tabG,
                const float* __restrict__ hitG, const float2* __restrict__ growG, uint2* __restrict__ out, int r0,
                uint32_t magic_tab, uint32_t magic_row, const __grid_constant__ GroundNormals GN
-#if FB_DENSITY_ROWS
-               , const float4* __restrict__ rowsG, const float4* __restrict__ rowsW
-#endif
                ) {
     typedef DensityCfg<ORDER2> C;
     constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
@@ -364,33 +296,6 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         tma_bulk_g2s(smem_raw, tabG + ((size_t)z * dd.tiles + tile) * DL * TT * ENT, TAB_B, bar);
     }
 
-#if FB_DENSITY_ROWS
-    // ---- row constants written by k_density_rows: texel geometry into geoS, the lane's 48 weights into registers
-    if (tid < TT) {
-        const int nui = tid >> dd.ms_shift, msl = tid & (dd.ms_tile - 1);
-        const int ms = tile * dd.ms_tile + msl;
-        float4 g = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        if (ms < P.scattering_mu_s_size) {
-            g = __ldg(rowsG + ((size_t)z * P.scattering_mu_size + y) * W + (nui * P.scattering_mu_s_size + ms));
-            g.w = __int_as_float(msl * dd.nu * ENT_B);                              // .w: byte offset of the texel's rows
-        }
-        geoS[tid] = g;
-    }
-    float Wr[DL], Wg[DL], Wb[DL];
-    {
-        const float4* wrow = rowsW + ((size_t)z * P.scattering_mu_size + y) * (DL * 32) + lane;
-#pragma unroll
-        for (int l = 0; l < DL; ++l) {
-            const float4 w = __ldg(wrow + l * 32);
-            Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
-        }
-    }
-    uint32_t gmask = 0;                                                        // theta rows that reach the ground (CTA-uniform)
-    for (int l = DL / 2; l < DL; ++l)
-        if (__ldg(hitG + (size_t)z * DL + l) != 0.f) gmask |= 1u << l;
-    (void)WtS;
-    __syncthreads();
-#else
     A<F> a(P);
     // ---- texel geometry, exact (scattering_density.comp:28-32) ------------------------------------------
     // One evaluation per thread: thread t < TT takes texel t of the tile; r and mu (functions of y, z only) come out of
@@ -452,7 +357,6 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         const float4 w = WtS[l * 32 + lane];
         Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
     }
-#endif
     // ---- work list ------------------------------------------------------------------------------------------
     // Every nu knot outside [mu mu_s - s, mu mu_s + s] is clamped onto the same bound (scattering.h:133-136), so a
     // texel whose (sx, sy, mu_s) equal those of the previous nu slice has bit-identical inputs: it is a FOLLOWER and
@@ -776,12 +680,6 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, hit, c.img.delta_irradiance, grow, r0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-#if FB_DENSITY_ROWS
-    float4* rowsG = reinterpret_cast<float4*>(tab + density_base_floats(P));
-    float4* rowsW = rowsG + (size_t)P.scattering_r_size * P.scattering_mu_size * W;
-    k_density_rows<<<dim3(P.scattering_mu_size, r1 - r0), 256, 0, c.stream>>>(P, c.trig, rowsG, rowsW, r0);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-#endif
     // from here on nothing reads delta_irradiance: indirect_irradiance may run concurrently with the main kernel
     if (after_prep && (e = cudaEventRecord(after_prep, c.stream)) != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -807,9 +705,6 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
         dim3 gm(d.tiles, P.scattering_mu_size, nz_);
         k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, hit, grow, c.img.scattering_density, zc,
                                                                       0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u, gn
-#if FB_DENSITY_ROWS
-                                                                      , rowsG, rowsW
-#endif
                                                                       );
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -1107,150 +1002,6 @@ __global__ void __launch_bounds__(256) k_single_scattering(const __grid_constant
     S[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, mie.x.v);
 }
 
-// -DFB_SS_TPT2=1 (staged for round 2, not the default build): the STAGED body above with two texels per thread
-// (128-thread CTAs, 8 per SM, half-size slab) and the node loop outside the texel loop, so that one broadcast load of
-// a node record (10 words in the sample pass, 6 in the staging pass -- as much data-pipe time as the two slab taps)
-// serves two texels / two staged columns.  Per texel the arithmetic and the order of the sum over the nodes are
-// unchanged: bit-identical tables.
-#ifndef FB_SS_TPT2
-#define FB_SS_TPT2 0
-#endif
-#if FB_SS_TPT2
-__global__ void __launch_bounds__(128, 8) k_single_scattering_t2(const __grid_constant__ FbParams P, Tex2 T, uint2* __restrict__ dR,
-                                                                  uint2* __restrict__ dM, uint2* __restrict__ S, int r0, int CH) {
-    constexpr int TPT = 2, NT = 128;
-    __shared__ SingleNode nodes[NS];
-    __shared__ float s_dx;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* slab = reinterpret_cast<float4*>(smem_raw);
-    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    const int xb = blockIdx.x * (TPT * NT), y = blockIdx.y, z = r0 + blockIdx.z;
-    A<F> a(P);
-    F r, mu;
-    bool hits;
-    float r_mu_s[TPT], nuf[TPT];
-    bool active[TPT];
-#pragma unroll
-    for (int k = 0; k < TPT; ++k) {
-        const int x = xb + threadIdx.x + k * NT;
-        F mu_s, nu;
-        a.TexelToRMuMuSNu((unsigned)min(x, W - 1), (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hits);   // r, mu, hits: functions of (y, z)
-        r_mu_s[k] = (r * mu_s).v; nuf[k] = nu.v; active[k] = x < W;
-    }
-    const F H = f_sqrt(a.top() * a.top() - a.bottom() * a.bottom());
-    {   // node records: threads i and 64 + i share node i (as in k_single_scattering)
-        const int j = threadIdx.x, i = j & 63;
-        if (i < NS) {
-            const bool partA = j < 64, partB = j >= 64;
-            const F dx = a.DistanceToNearest(r, mu, hits) / F(50.f);
-            const F d = F((float)i) * dx;
-            if (partA) {
-                const V tr = a.Transmittance(T, r, mu, d, hits);                            // :19-21
-                nodes[i].t.x = tr.x.v; nodes[i].t.y = tr.y.v; nodes[i].t.z = tr.z.v;
-                if (i == 0) s_dx = dx.v;
-            }
-            if (partB) {
-                const F r_d = a.ClampRadius(f_sqrt(d * d + F(2.f) * r * mu * d + r * r));  // single_scattering.comp:16
-                nodes[i].g0 = make_float4(d.v, (F(1.f) / r_d).v, r_d.v, (r_d * r_d).v);
-                const F rho = A<F>::SafeSqrt(r_d * r_d - a.bottom() * a.bottom());          // transmittance.h:14
-                const F d_min = a.top() - r_d, d_max = rho + H;
-                const F v = A<F>::CoordFromUnit(rho / H, P.transmittance_r_size);           // transmittance.h:21-23
-                int y0, y1;
-                F fy;
-                tex_axis(v, P.transmittance_r_size, y0, y1, fy);
-                nodes[i].row0 = y0 * P.transmittance_mu_size; nodes[i].row1 = y1 * P.transmittance_mu_size;
-                const F sin_h = a.bottom() / r_d;                                           // transmittance.h:67-73
-                const F cos_h = -f_sqrt(f_max(F(1.f) - sin_h * sin_h, F(0.f)));
-                const F al = F(P.sun_angular_radius);
-                const F e0 = -sin_h * al, e1 = sin_h * al;
-                nodes[i].g1 = make_float4(d_min.v, (F(1.f) / (d_max - d_min)).v, (cos_h + e0).v, (F(1.f) / (e1 - e0)).v);
-                nodes[i].t.w = fy.v;
-                const F w = (i == 0 || i == NS - 1) ? F(0.5f) : F(1.f);
-                nodes[i].rho_r = (A<F>::ProfileDensity(P.rayleigh_density, r_d - a.bottom()) * w).v;   // :24-27
-                nodes[i].rho_m = (A<F>::ProfileDensity(P.mie_density, r_d - a.bottom()) * w).v;
-            }
-        }
-    }
-    const float tt = P.top_radius * P.top_radius;
-    const int TW = P.transmittance_mu_size;
-    const float un = (float)(TW - 1);
-    const float umax = __int_as_float(__float_as_int(un) - 1);
-    float rsr[TPT], rsg[TPT], rsb[TPT], msr[TPT], msg[TPT], msb[TPT];
-#pragma unroll
-    for (int k = 0; k < TPT; ++k) rsr[k] = rsg[k] = rsb[k] = msr[k] = msg[k] = msb[k] = 0.f;
-    for (int c0 = 0; c0 < NS; c0 += CH) {
-        const int cn = min(CH, NS - c0);
-        __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
-        for (int jb = 0; jb < TW; jb += TPT * NT) {
-            for (int e0 = 0; e0 < cn; e0 += 2) {
-                float4 ra[2][TPT], rb[2][TPT];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {     // 8 row loads in flight per thread
-                    const SingleNode& n = nodes[c0 + min(e0 + u, cn - 1)];
-                    const int row0 = n.row0, row1 = n.row1;
-#pragma unroll
-                    for (int q = 0; q < TPT; ++q) {
-                        const int j = min(jb + (int)threadIdx.x + q * NT, TW - 1);
-                        ra[u][q] = __ldg(T.p + row0 + j); rb[u][q] = __ldg(T.p + row1 + j);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (e0 + u < cn) {
-                        const float4 nt = nodes[c0 + e0 + u].t;
-#pragma unroll
-                        for (int q = 0; q < TPT; ++q) {
-                            const int j = jb + (int)threadIdx.x + q * NT;
-                            if (j < TW)
-                                slab[(e0 + u) * TW + j] = make_float4(fmaf(nt.w, rb[u][q].x - ra[u][q].x, ra[u][q].x) * nt.x,
-                                                                      fmaf(nt.w, rb[u][q].y - ra[u][q].y, ra[u][q].y) * nt.y,
-                                                                      fmaf(nt.w, rb[u][q].z - ra[u][q].z, ra[u][q].z) * nt.z, 0.f);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int e = 0; e < cn; ++e) {
-            const int i = c0 + e;
-            const float4 g0 = nodes[i].g0, g1 = nodes[i].g1;
-            const float rr = nodes[i].rho_r, rm = nodes[i].rho_m;
-#pragma unroll
-            for (int k = 0; k < TPT; ++k) {
-                if (active[k]) {
-                    const float mu_s_d = fminf(fmaxf(fmaf(g0.x, nuf[k], r_mu_s[k]) * g0.y, -1.f), 1.f);   // :17
-                    const float disc = fmaf(g0.w, fmaf(mu_s_d, mu_s_d, -1.f), tt);                        // params.h:105-110
-                    const float dtop = fmaxf(fmaf(-g0.z, mu_s_d, sqrt_fast(fmaxf(disc, 0.f))), 0.f);
-                    const float tu = fminf(fmaxf((dtop - g1.x) * g1.y * un, 0.f), umax);                  // transmittance.h:20-22
-                    const float tm = __fadd_rd(tu, 8388608.f);
-                    const int j = __float_as_int(tm) - 0x4B000000;
-                    const float fx = tu - (tm - 8388608.f);
-                    const float4 p0 = slab[e * TW + j], p1 = slab[e * TW + j + 1];
-                    float sm = fminf(fmaxf((mu_s_d - g1.z) * g1.w, 0.f), 1.f);                            // transmittance.h:71-73
-                    sm = sm * sm * fmaf(-2.f, sm, 3.f);
-                    const float tr_ = fmaf(fx, p1.x - p0.x, p0.x) * sm, tg_ = fmaf(fx, p1.y - p0.y, p0.y) * sm, tb_ = fmaf(fx, p1.z - p0.z, p0.z) * sm;
-                    rsr[k] = fmaf(tr_, rr, rsr[k]); rsg[k] = fmaf(tg_, rr, rsg[k]); rsb[k] = fmaf(tb_, rr, rsb[k]);
-                    msr[k] = fmaf(tr_, rm, msr[k]); msg[k] = fmaf(tg_, rm, msg[k]); msb[k] = fmaf(tb_, rm, msb[k]);
-                }
-            }
-        }
-    }
-    const F dx = F(s_dx);
-#pragma unroll
-    for (int k = 0; k < TPT; ++k) {
-        const int x = xb + threadIdx.x + k * NT;
-        if (x >= W) continue;
-        const V ray = V(F(rsr[k]), F(rsg[k]), F(rsb[k])) * dx * V(P.solar_irradiance) * V(P.rayleigh_scattering);   // :62-64
-        const V mie = V(F(msr[k]), F(msg[k]), F(msb[k])) * dx * V(P.solar_irradiance) * V(P.mie_scattering);
-        const size_t o = ((size_t)z * P.scattering_mu_size + y) * W + x;
-        dR[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, 0.f);
-        dM[o] = pack_half4(mie.x.v, mie.y.v, mie.z.v, 0.f);
-        S[o] = pack_half4(ray.x.v, ray.y.v, ray.z.v, mie.x.v);
-    }
-}
-#endif
-
 cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
     const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
     const int nt = W >= 256 ? 256 : ((W + 31) / 32) * 32;
@@ -1264,38 +1015,15 @@ cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1) {
         k_single_scattering<false><<<g, nt, 0, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, 0);
         return cudaGetLastError();
     }
-#if FB_SS_TPT2
-    if (W % 256 == 0 && TW <= 256) {              // 128 threads x 2 texels, half the slab so that 8 CTAs fit an SM
-        const int ch2 = 1536 / TW < 1 ? 1 : 1536 / TW;
-        const size_t smem2 = (size_t)ch2 * TW * sizeof(float4);
-        cudaError_t e2 = cudaFuncSetAttribute(k_single_scattering_t2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        if (e2 != cudaSuccess) return e2;
-        k_single_scattering_t2<<<dim3(W / 256, c.P.scattering_mu_size, r1 - r0), 128, smem2, c.stream>>>(
-            c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, ch2);
-        return cudaGetLastError();
-    }
-#endif
     cudaError_t e = cudaFuncSetAttribute(k_single_scattering<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_single_scattering<true><<<g, nt, smem, c.stream>>>(c.P, texT(c), c.img.delta_rayleigh, c.img.delta_mie, c.img.scattering, r0, CH);
     return cudaGetLastError();
 }
 
-// -DFB_MS_DIET=1 (staged for round 2, not the default build): the staging half of a node record shrinks from two
-// broadcast LDS.128 (four weights, four row offsets) to one (first row offset, the two row steps, the two cell
-// fractions); the weights are rebuilt per thread by the same fp32 operations on the same operands (1 - f, four
-// products), the offsets by integer adds, so the staged entries are bit-identical.  A broadcast load costs a
-// data-pipe cycle per 4 bytes per lane like any other, and that pipe is what binds this kernel.
-#ifndef FB_MS_DIET
-#define FB_MS_DIET 0
-#endif
 struct MultiNode {       // per trapezoid node, block-uniform; 16-byte words so each is one (broadcast) LDS.128
-#if FB_MS_DIET
-    uint4 st;            // offset of row (y0, z0), (y1 - y0) * W | ((z1 - z0) * mu_size * W in .y), fy bits (.z), fz bits (.w)
-#else
     float4 w;            // bilinear weights of the (mu, r) cell of GetScattering(r_i, mu_i, ., ., hits): (y0z0, y1z0, y0z1, y1z1)
     uint4 off;           // texel offsets of those four rows in the density table
-#endif
     float4 t;            // GetTransmittance(r, mu, d_i) * dx * trapezoid weight (rgb), node distance d_i
     float inv_r, pad0, pad1, pad2;   // 1 / r_i
 };
@@ -1310,16 +1038,8 @@ struct MultiNode {       // per trapezoid node, block-uniform; 16-byte words so 
 #ifndef FB_MS_CU
 #define FB_MS_CU 4       // unroll of the per-texel node loop
 #endif
-// -DFB_MS_TPT2=1 (staged for round 2, not the default build): default-width rows run as 128-thread CTAs with two texels
-// per thread and 8 CTAs per SM.  The node records are CTA-uniform, but a broadcast LDS still costs one data-pipe cycle
-// per 4 bytes per lane (tools/lds_bench.cu): per warp and node, 5 wavefronts in the sample loop and 8 in the staging
-// loop next to ~10 for the two slab taps (tools/analyze_ms_banks.py).  Two texels per thread halve the record loads per
-// sample; the per-texel arithmetic and its order are unchanged, so the results are bit-identical.
-#ifndef FB_MS_TPT2
-#define FB_MS_TPT2 0
-#endif
 template <int TPT, int NTMAX>   // TPT texels per thread: the CTA covers the whole (nu, mu_s) row, W <= TPT * blockDim.x
-__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 128 ? 8 : 1)) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
+__global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : 1) k_multiple_scattering(const __grid_constant__ FbParams P, Tex2 T, const uint2* __restrict__ dens,
                                                               uint2* __restrict__ dMS, uint2* __restrict__ S, int r0, int CH) {
     constexpr int CU = FB_MS_CU;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1407,18 +1127,10 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
             F fy, fz;
             tex_axis(uvwz[2], P.scattering_mu_size, y0, y1, fy);
             tex_axis(uvwz[3], P.scattering_r_size, z0, z1, fz);
-#if FB_MS_DIET
-            // the two row steps fit 16 bits each only for small tables: keep them as full words, (dy, dz) in .y's halves
-            // would not; .y carries dy * W, the z step is rebuilt from the flag in its top bit
-            nodes[i].st = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W),
-                                     (unsigned)((y1 - y0) * W) | ((unsigned)(z1 - z0) << 31),
-                                     __float_as_uint(fy.v), __float_as_uint(fz.v));
-#else
             const float gy = 1.f - fy.v, gz = 1.f - fz.v;
             nodes[i].w = make_float4(gy * gz, fy.v * gz, gy * fz.v, fy.v * fz.v);
             nodes[i].off = make_uint4((unsigned)((z0 * P.scattering_mu_size + y0) * W), (unsigned)((z0 * P.scattering_mu_size + y1) * W),
                                       (unsigned)((z1 * P.scattering_mu_size + y0) * W), (unsigned)((z1 * P.scattering_mu_size + y1) * W));
-#endif
             nodes[i].inv_r = (F(1.f) / r_i).v; nodes[i].pad0 = nodes[i].pad1 = nodes[i].pad2 = 0.f;
         }
     }
@@ -1430,120 +1142,6 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
     // u * MS - 0.5 with u = 0.5/MS + xx * (1 - 1/MS)  ==  xx * (MS - 1)
     const float msm1 = (float)(MS - 1);
     const float tmax = __int_as_float(__float_as_int(msm1) - 1);
-#if FB_MS_TPT2
-    if constexpr (NTMAX == 128) {                 // the two-texel CTAs of default-width rows only
-    // Node loop outside, the thread's TPT texels inside: one (broadcast) record load serves all of them.  Per texel the
-    // staged entries and the order of the accumulation over the nodes are those of the loop in the #else branch.
-    bool actk[TPT];
-    bool act_any = false, two_any = false;
-#pragma unroll
-    for (int k = 0; k < TPT; ++k) {
-        const int xk = threadIdx.x + k * blockDim.x;
-        actk[k] = xk < W && leader[k] == xk;
-        act_any |= actk[k];
-        two_any |= actk[k] && two[k];
-    }
-    const bool warp_act = __any_sync(0xffffffffu, act_any);      // warp-uniform
-    const bool warp_two = __any_sync(0xffffffffu, two_any);
-    for (int c0 = 0; c0 < NS; c0 += CH) {
-        const int cn = min(CH, NS - c0);
-        __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
-        constexpr int U2 = 2;                     // nodes in flight: U2 * TPT * 4 row loads per thread
-        for (int e0 = 0; e0 < cn; e0 += U2) {
-            uint2 raw[U2][TPT][4];
-#if FB_MS_DIET
-            float2 frac[U2];
-            const uint32_t zstep = (uint32_t)P.scattering_mu_size * (uint32_t)W;
-#endif
-#pragma unroll
-            for (int u = 0; u < U2; ++u) {
-#if FB_MS_DIET
-                const uint4 st = nodes[c0 + min(e0 + u, cn - 1)].st;
-                const uint32_t dy = st.y & 0x7fffffffu, dz = (st.y >> 31) ? zstep : 0u;
-                const uint4 o = make_uint4(st.x, st.x + dy, st.x + dz, st.x + dz + dy);
-                frac[u] = make_float2(__uint_as_float(st.z), __uint_as_float(st.w));
-#else
-                const uint4 o = nodes[c0 + min(e0 + u, cn - 1)].off;
-#endif
-#pragma unroll
-                for (int k = 0; k < TPT; ++k) {
-                    const uint32_t xi = (uint32_t)min((int)(threadIdx.x + k * blockDim.x), W - 1);
-                    raw[u][k][0] = __ldg(dens + (o.x + xi)); raw[u][k][1] = __ldg(dens + (o.y + xi));
-                    raw[u][k][2] = __ldg(dens + (o.z + xi)); raw[u][k][3] = __ldg(dens + (o.w + xi));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U2; ++u) {
-                if (e0 + u < cn) {
-#if FB_MS_DIET
-                    const float gy = 1.f - frac[u].x, gz = 1.f - frac[u].y;
-                    const float4 w = make_float4(gy * gz, frac[u].x * gz, gy * frac[u].y, frac[u].x * frac[u].y);
-#else
-                    const float4 w = nodes[c0 + e0 + u].w;
-#endif
-#pragma unroll
-                    for (int k = 0; k < TPT; ++k) {
-                        const int x = threadIdx.x + k * blockDim.x;
-                        if (x < W) {
-                            const float4 a00 = unpack_half4(raw[u][k][0]), a10 = unpack_half4(raw[u][k][1]);
-                            const float4 a01 = unpack_half4(raw[u][k][2]), a11 = unpack_half4(raw[u][k][3]);
-                            float4 v;
-                            v.x = fmaf(a11.x, w.w, fmaf(a01.x, w.z, fmaf(a10.x, w.y, a00.x * w.x)));
-                            v.y = fmaf(a11.y, w.w, fmaf(a01.y, w.z, fmaf(a10.y, w.y, a00.y * w.x)));
-                            v.z = fmaf(a11.z, w.w, fmaf(a01.z, w.z, fmaf(a10.z, w.y, a00.z * w.x)));
-                            v.w = 0.f;
-                            slab[(e0 + u) * W + x] = v;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (warp_act) {
-#define FB_MS_BODY(k, TWO)                                                                                                  \
-            if (actk[k]) {                                                                                                  \
-                const float mus_i = fminf(fmaxf(fmaf(nt.w, nuf[k], rmus[k]) * inv_r, -1.f), 1.f);       /* :38 */           \
-                const float dd = fmaf(-bot, mus_i, sqrt_fast(fmaf(b2, mus_i * mus_i, H2)));                                 \
-                const float aa = (dd - dmin) * inv_span;                                                                    \
-                const float xx = fmaxf(fmaf(aa, minvA, 1.f), 0.f) * rcp_fast(1.f + aa);                                     \
-                const float t = fminf(fmaxf(xx * msm1, 0.f), tmax);                                                         \
-                const float tm = __fadd_rd(t, 8388608.f);                                                                   \
-                const int j = __float_as_int(tm) - 0x4B000000;                                                              \
-                const float fx = t - (tm - 8388608.f);                                                                      \
-                const float4* s = slab + e * W + j;                                                                         \
-                const float4 p00 = s[kx0[k]], p01 = s[kx0[k] + 1];                                                          \
-                float vr = fmaf(fx, p01.x - p00.x, p00.x), vg = fmaf(fx, p01.y - p00.y, p00.y), vb = fmaf(fx, p01.z - p00.z, p00.z); \
-                if (TWO) {                                                                                                  \
-                    const float4 p10 = s[kx1[k]], p11 = s[kx1[k] + 1];                                                      \
-                    const float v1r = fmaf(fx, p11.x - p10.x, p10.x), v1g = fmaf(fx, p11.y - p10.y, p10.y), v1b = fmaf(fx, p11.z - p10.z, p10.z); \
-                    vr = fmaf(ln[k], v1r - vr, vr); vg = fmaf(ln[k], v1g - vg, vg); vb = fmaf(ln[k], v1b - vb, vb);         \
-                }                                                                                                           \
-                ar[k] = fmaf(vr, nt.x, ar[k]);                                                                              \
-                ag[k] = fmaf(vg, nt.y, ag[k]);                                                                              \
-                ab[k] = fmaf(vb, nt.z, ab[k]);                                                                              \
-            }
-            if (warp_two) {
-#pragma unroll 2
-                for (int e = 0; e < cn; ++e) {
-                    const float4 nt = nodes[c0 + e].t;
-                    const float inv_r = nodes[c0 + e].inv_r;
-#pragma unroll
-                    for (int k = 0; k < TPT; ++k) FB_MS_BODY(k, two[k])
-                }
-            } else {
-#pragma unroll 2
-                for (int e = 0; e < cn; ++e) {
-                    const float4 nt = nodes[c0 + e].t;
-                    const float inv_r = nodes[c0 + e].inv_r;
-#pragma unroll
-                    for (int k = 0; k < TPT; ++k) FB_MS_BODY(k, false)
-                }
-            }
-#undef FB_MS_BODY
-        }
-    }
-    } else {
-#endif
     for (int c0 = 0; c0 < NS; c0 += CH) {
         const int cn = min(CH, NS - c0);
         __syncthreads();                          // nodes ready (first pass) / previous chunk consumed
@@ -1557,33 +1155,16 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
                 // left the loop waiting on L2 latency every iteration).
                 for (int e0 = 0; e0 < cn; e0 += FB_MS_U) {
                     uint2 raw[FB_MS_U][4];
-#if FB_MS_DIET
-                    float2 frac[FB_MS_U];
-                    const uint32_t zstep = (uint32_t)P.scattering_mu_size * (uint32_t)W;
-#endif
 #pragma unroll
                     for (int u = 0; u < FB_MS_U; ++u) {
-#if FB_MS_DIET
-                        const uint4 st = nodes[c0 + min(e0 + u, cn - 1)].st;
-                        const uint32_t dy = st.y & 0x7fffffffu, dz = (st.y >> 31) ? zstep : 0u;
-                        const uint4 o = make_uint4(st.x, st.x + dy, st.x + dz, st.x + dz + dy);
-                        frac[u] = make_float2(__uint_as_float(st.z), __uint_as_float(st.w));
-#else
                         const uint4 o = nodes[c0 + min(e0 + u, cn - 1)].off;   // 32-bit texel indices: one IMAD.WIDE per address
-#endif
                         raw[u][0] = __ldg(dens + (o.x + xi)); raw[u][1] = __ldg(dens + (o.y + xi));
                         raw[u][2] = __ldg(dens + (o.z + xi)); raw[u][3] = __ldg(dens + (o.w + xi));
                     }
 #pragma unroll
                     for (int u = 0; u < FB_MS_U; ++u) {
                         if (e0 + u < cn) {
-#if FB_MS_DIET
-                            // frac[u] belongs to node min(e0 + u, cn - 1) == e0 + u here
-                            const float gy = 1.f - frac[u].x, gz = 1.f - frac[u].y;
-                            const float4 w = make_float4(gy * gz, frac[u].x * gz, gy * frac[u].y, frac[u].x * frac[u].y);
-#else
                             const float4 w = nodes[c0 + e0 + u].w;
-#endif
                             const float4 a00 = unpack_half4(raw[u][0]), a10 = unpack_half4(raw[u][1]);
                             const float4 a01 = unpack_half4(raw[u][2]), a11 = unpack_half4(raw[u][3]);
                             float4 v;
@@ -1640,9 +1221,6 @@ __global__ void __launch_bounds__(NTMAX, NTMAX == 256 ? FB_MS_MINB : (NTMAX == 1
             }
         }
     }
-#if FB_MS_TPT2
-    }
-#endif
     __syncthreads();                              // last chunk consumed: the slab now carries the leaders' results
 #pragma unroll
     for (int k = 0; k < TPT; ++k) {
@@ -1683,12 +1261,6 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
     const size_t smem = sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4);
     if (smem > 200 * 1024) return ref::multiple_scattering(c, r0, r1);
-#if FB_MS_TPT2
-    if (W == 256) {                               // 128 threads x 2 texels, half the slab so that 8 CTAs fit an SM
-        const int ch2 = 1536 / W;
-        return multiple_launch<2, 128>(c, 128, ch2, sizeof(MultiNode) * NS + (size_t)ch2 * W * sizeof(float4), r0, r1);
-    }
-#endif
     if (nt <= 256) return multiple_launch<1, 256>(c, nt, CH, smem, r0, r1);
     if (tpt == 1) return multiple_launch<1, 1024>(c, nt, CH, smem, r0, r1);
     if (tpt == 2) return multiple_launch<2, 1024>(c, nt, CH, smem, r0, r1);
@@ -1698,7 +1270,7 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
 
 int launches_per_stage(const FbParams& P, int stage, int r_count) {
     if (stage != FB_STAGE_SCATTERING_DENSITY || !density_supported(P)) return 1;
-    return 1 + FB_DENSITY_ROWS + (r_count + GN_MAXR - 1) / GN_MAXR;   // preparation (+ row constants) + one main launch per GN_MAXR levels
+    return 1 + (r_count + GN_MAXR - 1) / GN_MAXR;   // preparation + one main launch per GN_MAXR levels
 }
 
 }  // namespace fast

@@ -1,5 +1,7 @@
-"""The variants staged behind compile-time flags (README.md "Staged for round 2") must keep compiling for sm_100a:
-nvcc cross-compiles here without a GPU.  Objects go to a temporary directory; the product library is not touched."""
+"""The one remaining A/B build flag (-DFB_RENDER_IEEE_GUARDS=1: every division / square root of the sky evaluation in
+its guarded IEEE form, the cross-check of tools/render_ab.py) must keep compiling for sm_100a: nvcc cross-compiles here
+without a GPU.  Objects go to a temporary directory; the product library is not touched.  The variants staged in
+round 1 were settled on a B200 in round 2 (profiles/r2_staged_variants_ab.txt): winners adopted, losers deleted."""
 import os
 import shutil
 import subprocess
@@ -11,9 +13,7 @@ CSRC = os.path.join(ROOT, "fuzzyblue_b200", "csrc")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
 
-CASES = [("fb_render.cu", ["-DFB_RENDER_SKY_SPLIT=1", "-DFB_RENDER_MAGIC_FLOOR=1"]),
-         ("fb_render.cu", ["-DFB_RENDER_IEEE_GUARDS=1"]),
-         ("fb_kernels_fast.cu", ["-DFB_MS_DIET=1", "-DFB_MS_TPT2=1", "-DFB_SS_TPT2=1", "-DFB_DENSITY_ROWS=1"])]
+CASES = [("fb_render.cu", ["-DFB_RENDER_IEEE_GUARDS=1"])]
 
 
 @pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not installed")
