@@ -21,6 +21,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-3
 F16_FLOOR = 2.0 ** -14
+SMALL_TABLE_OUTLIERS = 8      # values beyond 1e-3 tolerated end to end in a reduced-dims table (see check_compounded)
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FAMILIES = {"fast": api.KERNELS_FAST, "reference": api.KERNELS_REFERENCE}
 
@@ -42,16 +43,22 @@ def check(name, e):
     assert worst <= RTOL, f"{name}: max error {worst:.3e} at {where}"
 
 
-def check_compounded(name, e):
+def check_compounded(name, e, max_count=None):
     """End-to-end gate for 3-D tables downstream of scattering_density.  The reference stores scattering_density in
     fp16 where most of it is SUBNORMAL (values ~1e-6, spacing 2^-24 = 6e-8, i.e. 1 ulp = 6 %).  Two correct
     implementations that associate a 512-term sum differently flip that rounding on ~1e-4 of the texels, and the next
     multiple-scattering pass amplifies each flip to a per-cent-level change of the few texels whose rays cross it.
     No implementation (including the reference on two different drivers) can hold 1e-3 on *every* texel end to end;
-    the per-stage tests above do hold it, texel by texel, on identical inputs."""
-    frac = float((e > RTOL).mean())
-    print(f"{name}: max {e.max():.3e}, fraction beyond 1e-3: {frac:.2e}")
-    assert frac <= 2e-3 and e.max() <= 2e-2, f"{name}: max {e.max():.3e}, fraction beyond 1e-3 {frac:.2e}"
+    the per-stage tests above do hold it, texel by texel, on identical inputs.
+
+    Gate = what was measured on B200 with a 3x margin: at the default dims 9 of 1 048 576 texels
+    (8.6e-6) beyond 1e-3 with a maximum of 3.9e-3  ->  fraction <= 3e-5, maximum <= 1e-2.  Small tables get an
+    absolute allowance (`max_count` values) because one value of a 4096-texel table is already 6e-5 of it."""
+    n_out = int((e > RTOL).sum())
+    frac = n_out / e.size
+    print(f"{name}: max {e.max():.3e}, beyond 1e-3: {n_out} of {e.size} values ({frac:.2e})")
+    allowed = max(int(3e-5 * e.size), 0 if max_count is None else max_count)
+    assert n_out <= allowed and e.max() <= 1e-2, f"{name}: max {e.max():.3e}, {n_out} values beyond 1e-3 (allowed {allowed})"
 
 
 @pytest.fixture(scope="module", params=list(FAMILIES))
@@ -167,7 +174,7 @@ def test_full_precompute(builder, case, family):
     check("transmittance", err32(atm.read_transmittance(), ref.transmittance))
     check("irradiance", err32(atm.read_irradiance(), ref.irradiance))
     S = atm.read_scattering()
-    (check if family == "reference" else check_compounded)("scattering", err16(S, ref.scattering))
+    (check if family == "reference" else (lambda n, e: check_compounded(n, e, max_count=SMALL_TABLE_OUTLIERS)))("scattering", err16(S, ref.scattering))
     # single-Mie red channel survives the later orders bit for bit (multiple_scattering.comp:92 adds 0)
     assert np.array_equal(S[..., 3], single_mie_red)
     check("scattering.a == single Mie red", err16(S[..., 3], ref.delta_mie[..., 0]))
@@ -209,8 +216,8 @@ def test_tall_table(builder, oracle_tall_f32):
         pend.run_stage(api.STAGE_SCATTERING_DENSITY, order=o)
         check(f"tall scattering_density(order {o})", err16(pend.download(api.IMAGE_SCATTERING_DENSITY), ref.history[o]["scattering_density"]))
     T, S, E = fb.precompute_host(builder, fb.Parameters(order=order, **dims))
-    check_compounded("tall scattering", err16(S, ref.scattering))
-    check_compounded("tall irradiance", err32(E, ref.irradiance))
+    check_compounded("tall scattering", err16(S, ref.scattering), max_count=SMALL_TABLE_OUTLIERS)
+    check_compounded("tall irradiance", err32(E, ref.irradiance), max_count=SMALL_TABLE_OUTLIERS)
 
 
 @pytest.mark.parametrize("index", [0, 1, 2])
@@ -231,7 +238,7 @@ def test_randomised_atmospheres(builder, family, index):
     T, S, E = fb.precompute_host(builder, p)
     check("transmittance", err32(T, ref.transmittance))
     check("irradiance", err32(E, ref.irradiance))
-    (check if family == "reference" else check_compounded)("scattering", err16(S, ref.scattering))
+    (check if family == "reference" else (lambda n, e: check_compounded(n, e, max_count=SMALL_TABLE_OUTLIERS)))("scattering", err16(S, ref.scattering))
 
 
 def test_resubmit_replays_the_same_tables(builder):
@@ -344,25 +351,53 @@ def default_tables(builder):
     return snap
 
 
-def test_default_dims_against_golden(default_tables, family):
-    """Default dims, 4 orders, end to end vs the committed oracle fixture: 2-D tables in full, 4096 seeded texels of
-    every 3-D table of every order."""
-    g = np.load(os.path.join(GOLDEN, "default_f32.npz"))
-    idx = g["idx"]
-    for name in ("transmittance", "irradiance", "direct_irradiance", "o2_delta_irradiance", "o3_delta_irradiance",
-                 "o4_delta_irradiance", "o2_irradiance", "o3_irradiance"):
-        check(name, err32(default_tables[name], g[name]))
-    for name in ("delta_rayleigh", "delta_mie", "o2_scattering_density"):
-        check(name, err16(default_tables[name].reshape(-1, 4)[idx], g[name]))
+def test_default_dims_every_texel_against_oracle(default_tables, family, oracle_default_f32):
+    """Default dims (BASELINE.json configs[1]), 4 orders, end to end against the fp32 oracle run in full at test time:
+    EVERY texel of every table of every order (round 1 compared 4096 seeded texels of a committed fixture).  The
+    2-D tables, single scattering and the first density pass are held to 1e-3 on every texel; everything downstream of
+    the fp16-subnormal density table to the end-to-end gate of check_compounded."""
+    ref = oracle_default_f32
+    H = ref.history
+    for name, want in (("transmittance", ref.transmittance), ("irradiance", ref.irradiance),
+                       ("direct_irradiance", H["single"]["delta_irradiance"]),
+                       ("o2_delta_irradiance", H[2]["delta_irradiance"]), ("o3_delta_irradiance", H[3]["delta_irradiance"]),
+                       ("o4_delta_irradiance", H[4]["delta_irradiance"]), ("o2_irradiance", H[2]["irradiance"]),
+                       ("o3_irradiance", H[3]["irradiance"])):
+        check(name, err32(default_tables[name], want))
+    for name, want in (("delta_rayleigh", ref.delta_rayleigh), ("delta_mie", ref.delta_mie),
+                       ("o2_scattering_density", H[2]["scattering_density"])):
+        check(name, err16(default_tables[name], want))
     # the contraction-free family tracks the oracle almost bit for bit and is held to 1e-3 everywhere
     gate = check if family == "reference" else check_compounded
-    for name in ("o3_scattering_density", "o4_scattering_density", "o2_delta_multiple_scattering",
-                 "o3_delta_multiple_scattering", "o4_delta_multiple_scattering", "o2_scattering", "o3_scattering", "scattering"):
-        gate(name, err16(default_tables[name].reshape(-1, 4)[idx], g[name]))
-    # information: distance of the final table from the fp64 ideal evaluation (not a gate — the reference's own fp32
-    # formulas sit several per cent from it on horizon-grazing rays, see DESIGN.md "Numerics")
-    e = err16(default_tables["scattering"].reshape(-1, 4)[idx], g["scattering_f64_ideal"])
-    print(f"scattering vs fp64 ideal: median {np.median(e):.2e} p99 {np.quantile(e, 0.99):.2e} max {e.max():.2e}")
+    for name, want in (("o3_scattering_density", H[3]["scattering_density"]), ("o4_scattering_density", H[4]["scattering_density"]),
+                       ("o2_delta_multiple_scattering", H[2]["delta_multiple_scattering"]),
+                       ("o3_delta_multiple_scattering", H[3]["delta_multiple_scattering"]),
+                       ("o4_delta_multiple_scattering", H[4]["delta_multiple_scattering"]),
+                       ("o2_scattering", H[2]["scattering"]), ("o3_scattering", H[3]["scattering"]), ("scattering", ref.scattering)):
+        gate(name, err16(default_tables[name], want))
+
+
+def test_default_dims_stagewise_against_oracle_every_texel(builder, oracle_default_f32):
+    """Default dims, every 3-D stage of every order run on the ORACLE's inputs (uploaded), every texel of the output
+    against the oracle's output: the per-stage 1e-3 statement at the benchmarked size, with no compounding."""
+    ref = oracle_default_f32
+    pend = staged(builder, {}, {api.IMAGE_TRANSMITTANCE: ref.transmittance})
+    pend.run_stage(api.STAGE_SINGLE_SCATTERING)
+    check("default delta_rayleigh", err16(pend.download(api.IMAGE_DELTA_RAYLEIGH), ref.delta_rayleigh))
+    check("default delta_mie", err16(pend.download(api.IMAGE_DELTA_MIE), ref.delta_mie))
+    for o in (2, 3, 4):
+        for image, host in inputs_of_order(ref, o).items():
+            pend.upload(image, host)
+        pend.run_stage(api.STAGE_SCATTERING_DENSITY, order=o)
+        check(f"default scattering_density(order {o})", err16(pend.download(api.IMAGE_SCATTERING_DENSITY), ref.history[o]["scattering_density"]))
+        pend.upload(api.IMAGE_SCATTERING_DENSITY, ref.history[o]["scattering_density"])
+        pend.run_stage(api.STAGE_INDIRECT_IRRADIANCE, order=o - 1)
+        check(f"default delta_irradiance(order {o})", err32(pend.download(api.IMAGE_DELTA_IRRADIANCE), ref.history[o]["delta_irradiance"]))
+        check(f"default irradiance(order {o})", err32(pend.download(api.IMAGE_IRRADIANCE), ref.history[o]["irradiance"]))
+        pend.run_stage(api.STAGE_MULTIPLE_SCATTERING)
+        check(f"default delta_multiple_scattering(order {o})",
+              err16(pend.download(api.IMAGE_DELTA_MULTIPLE_SCATTERING), ref.history[o]["delta_multiple_scattering"]))
+        check(f"default scattering(order {o})", err16(pend.download(api.IMAGE_SCATTERING), ref.history[o]["scattering"]))
 
 
 def test_default_dims_properties(default_tables):

@@ -222,3 +222,60 @@ def test_fast_family_hoisting_is_exact():
         c1, t1 = rF.draw_host(atm, views[k][0], views[k][1])
         assert np.array_equal(color[k].cpu().numpy(), c1, equal_nan=True)
         assert np.array_equal(transm[k].cpu().numpy(), t1, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The benchmarked configuration (BASELINE.json configs[4]): 3840x2160 frames of the 256-view sweep on the DEFAULT tables
+# ------------------------------------------------------------------------------------------------------------------
+W4K, H4K = 3840, 2160
+# views of synthetic.camera_sweep(256, 3840, 2160): two 1 m cameras, low / mid altitudes, the top boundary region and
+# four cameras in space (alt > 60 km: the `move the camera to the top boundary` branch, render_sky.h:120-136)
+VIEWS_4K = (193, 67, 5, 13, 26, 7, 0, 36, 100, 200)
+
+
+@pytest.fixture(scope="module")
+def default_scene():
+    import torch
+    builder = fb.Builder(0)
+    pend = fb.Atmosphere.build(builder, None, fb.Parameters())
+    torch.cuda.synchronize()
+    atm = pend.assert_ready()
+    return dict(builder=builder, atm=atm, T=atm.read_transmittance().astype(np.float64), S=atm.read_scattering().astype(np.float64),
+                renderer=fb.Renderer(builder), op=O.Params())
+
+
+def test_4k_sweep_views_match_oracle_on_default_tables(default_scene):
+    """Ten of the 256 sweep views at 3840x2160 on the default-dims tables the bench uses; the fp32 oracle evaluates a
+    1/64 pixel subset of each (every 8th column of every 8th row, offset by the view index so the subsets differ).
+    Sky pixels (depth 0, no cancelling subtraction): 1e-3 relative with a floor of 1e-5 of the frame's peak radiance;
+    geometry pixels (`scattering - T * scattering_p`, render_sky.h:178): the floor is 1e-3 of the frame peak."""
+    sc = default_scene
+    draws, extra = synthetic.camera_sweep(256, W4K, H4K)
+    n_space = n_ground = n_sky = 0
+    for k in VIEWS_4K:
+        depth = synthetic.analytic_depth(extra[k][0], extra[k][1], W4K, H4K)
+        color, transm = sc["renderer"].draw_host(sc["atm"], draws[k], depth)
+        ys, xs = np.meshgrid(np.arange(k % 8, H4K, 8), np.arange((3 * k) % 8, W4K, 8), indexing="ij")
+        idx = (ys * W4K + xs).reshape(-1)
+        d = draws[k]
+        oc, ot = O.render(sc["op"], O.F32, sc["T"], sc["S"], O.pack_draw(d.inverse_viewproj, d.camera_position, d.sun_direction),
+                          depth, idx=idx)
+        gc, gt = color.reshape(-1, 4)[idx].astype(np.float64), transm.reshape(-1, 4)[idx].astype(np.float64)
+        ground = depth.reshape(-1)[idx] > 0
+        undefined = ~np.isfinite(ot)                       # downward sky rays: the shader's own inf - inf (see above)
+        assert not ground[undefined.any(axis=-1)].any()
+        ot = np.where(undefined, gt, ot)
+        assert np.all(np.isfinite(oc)) and np.all(np.isfinite(gc)) and np.all(np.isfinite(gt))
+        peak = max(float(np.abs(oc).max()), 1e-3)
+        floor = np.where(ground, 1e-3 * peak, 1e-5 * peak)[:, None]
+        ec = np.abs(gc - oc) / np.maximum(np.abs(oc), floor)
+        et = np.abs(gt - ot) / np.maximum(np.abs(ot), 1e-6)
+        alt = d.camera_position[2] - 6360.0
+        print(f"view {k}: alt {alt:.3f} km, ground {ground.mean():.2f}, colour err max sky {ec[~ground].max() if (~ground).any() else 0:.2e} "
+              f"ground {ec[ground].max() if ground.any() else 0:.2e}, transmittance err max {et.max():.2e}")
+        assert ec.max() <= 1e-3, (k, float(ec.max()))
+        assert et.max() <= 1e-3, (k, float(et.max()))
+        n_space += alt > 60.0
+        n_ground += int(ground.sum())
+        n_sky += int((~ground).sum())
+    assert n_space >= 2 and n_ground > 100000 and n_sky > 100000
