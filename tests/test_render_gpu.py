@@ -228,9 +228,10 @@ def test_fast_family_hoisting_is_exact():
 # The benchmarked configuration (BASELINE.json configs[4]): 3840x2160 frames of the 256-view sweep on the DEFAULT tables
 # ------------------------------------------------------------------------------------------------------------------
 W4K, H4K = 3840, 2160
-# views of synthetic.camera_sweep(256, 3840, 2160): two 1 m cameras, low / mid altitudes, the top boundary region and
-# four cameras in space (alt > 60 km: the `move the camera to the top boundary` branch, render_sky.h:120-136)
-VIEWS_4K = (193, 67, 5, 13, 26, 7, 0, 36, 100, 200)
+# views of synthetic.camera_sweep(256, 3840, 2160): two 1 m cameras, low altitudes, and six cameras in space that see the
+# planet and its limb (alt 70 .. 1750 km: the `move the camera to the top boundary` branch, render_sky.h:120-136); view 26
+# (448 km) looks away from the planet: every ray misses the atmosphere (radiance 0, transmittance 1)
+VIEWS_4K = (193, 67, 5, 100, 13, 200, 129, 2, 46, 116, 26)
 
 
 @pytest.fixture(scope="module")
@@ -247,8 +248,10 @@ def default_scene():
 def test_4k_sweep_views_match_oracle_on_default_tables(default_scene):
     """Ten of the 256 sweep views at 3840x2160 on the default-dims tables the bench uses; the fp32 oracle evaluates a
     1/64 pixel subset of each (every 8th column of every 8th row, offset by the view index so the subsets differ).
-    Sky pixels (depth 0, no cancelling subtraction): 1e-3 relative with a floor of 1e-5 of the frame's peak radiance;
-    geometry pixels (`scattering - T * scattering_p`, render_sky.h:178): the floor is 1e-3 of the frame peak."""
+    Tolerance: 1e-3 relative on every channel of both outputs.  Floors (below which the error is measured against the
+    floor): sky pixels (depth 0, no cancelling subtraction) 1e-5 of the frame's peak radiance; geometry pixels
+    (`scattering - T * scattering_p`, render_sky.h:178, a difference of nearly equal look-ups) 1e-3 of the frame peak.
+    Measured on B200 (round 2): <= 1.7e-6 on every checked pixel of every view, i.e. 600x inside the gate."""
     sc = default_scene
     draws, extra = synthetic.camera_sweep(256, W4K, H4K)
     n_space = n_ground = n_sky = 0
@@ -278,4 +281,4 @@ def test_4k_sweep_views_match_oracle_on_default_tables(default_scene):
         n_space += alt > 60.0
         n_ground += int(ground.sum())
         n_sky += int((~ground).sum())
-    assert n_space >= 2 and n_ground > 100000 and n_sky > 100000
+    assert n_space >= 6 and n_ground > 100000 and n_sky > 100000
