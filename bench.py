@@ -11,9 +11,14 @@ device_wait_idle), at the default dims of BASELINE.json configs[1] instead of th
 At N > 1 every rank builds its own atmosphere per step (independent atmospheres shard with no data-path collective,
 SURVEY.md §8e) and `value` is the time per atmosphere over the whole job: weak scaling.
 
-Prints ONE JSON line (rank 0).  Extra objects: `roofline` (dominant kernel: scattering_density), `cpu_baseline`
-(the CPU oracle port, bounded sample), `render` (the second half of BASELINE.json's metric: sky evaluation Mpixel/s at
-3840x2160), `e2e` (host-buffer path through the C ABI), `clocks`.
+Prints ONE JSON line (rank 0).  Extra objects, at every N:
+  `render`  the second half of BASELINE.json's metric: sky evaluation Mpixel/s at 3840x2160 over the 256-view sweep
+            (configs[4]); at N > 1 the views are split rank::N, the 8.25 MiB tables are built per rank, no collective;
+  `hires`   BASELINE.json configs[2]: ONE high-resolution atmosphere (2 GiB per 3-D table, 8 orders) built by all N
+            ranks through fb_pending_run_sharded -- the configuration that communicates (one all-gather of
+            scattering_density per order, one-slice halos, irradiance rows over NCCL): strong scaling, with the bytes;
+and at N = 1: `roofline` (dominant kernel: scattering_density), `cpu_baseline` (the CPU oracle port: ONE full
+default-dims precompute, every texel, measured), `e2e` (host-buffer path through the C ABI), `clocks`.
 """
 from __future__ import annotations
 
@@ -87,43 +92,32 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port (fp32 mode = the shaders as written) on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_precompute_ms(stride: int):
-    """Estimated full default-dims 4-order precompute on the CPU oracle from a bounded sample: the 2-D stages in full,
-    every 3-D stage on every `stride`-th texel (seeded offset), scaled by `stride`."""
-    import numpy as np
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_precompute_ms():
+    """ONE full default-dims 4-order precompute on the CPU oracle (fp32 mode = the shaders as written): real tables,
+    every texel of every stage, OpenMP over all host cores.  A measurement, not an extrapolation."""
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core.  libgomp reads
     # the variable when the oracle library is first loaded.
     if "oracle.oracle" not in sys.modules:
         os.environ["OMP_NUM_THREADS"] = str(host_cores())
     from oracle import oracle as O
     O.set_threads(host_cores())
-    p = O.Params()
-    n_tex = int(np.prod(p.s_shape[:3]))
-    idx = np.arange(stride // 2, n_tex, stride, dtype=np.int64)
-    t = {}
-
-    def timed(name, fn):
-        t0 = time.perf_counter()
-        out = fn()
-        t[name] = time.perf_counter() - t0
-        return out
-
-    T = timed("transmittance", lambda: O.transmittance(p, O.F32))
-    dE = timed("direct_irradiance", lambda: O.direct_irradiance(p, O.F32, T))
-    timed("single_scattering", lambda: O.single_scattering(p, O.F32, T, idx))
-    # the 3-D inputs of the later stages only steer values, not the amount of work: smooth synthetic tables
-    flat = np.full(p.s_shape, 1e-2)
-    timed("density_o2", lambda: O.scattering_density(p, O.F32, 2, T, flat, flat, flat, dE, idx))
-    timed("density_o3", lambda: O.scattering_density(p, O.F32, 3, T, flat, flat, flat, dE, idx))
-    timed("indirect_o1", lambda: O.indirect_irradiance(p, O.F32, 1, flat, flat, flat, np.zeros(p.e_shape)))
-    timed("indirect_o2", lambda: O.indirect_irradiance(p, O.F32, 2, flat, flat, flat, np.zeros(p.e_shape)))
-    timed("multiple", lambda: O.multiple_scattering(p, O.F32, T, flat, flat, idx))
-    scale = n_tex / idx.size
-    total = (t["transmittance"] + t["direct_irradiance"] + scale * t["single_scattering"] + scale * t["density_o2"]
-             + 2 * scale * t["density_o3"] + t["indirect_o1"] + 2 * t["indirect_o2"] + 3 * scale * t["multiple"])
-    sample = (f"oracle fp32 port (not lavapipe): 2-D stages in full, 3-D stages on every {stride}th texel "
-              f"({idx.size} of {n_tex}) scaled x{scale:.0f}; {sum(t.values()):.1f} s of CPU wall time")
-    return total * 1e3, sample
+    t0 = time.perf_counter()
+    tables = O.precompute(O.Params(), O.F32)
+    dt = time.perf_counter() - t0
+    ok = bool((tables.scattering[..., :3] >= 0).all()) and float(tables.irradiance.max()) > 0
+    sample = (f"oracle fp32 port (not lavapipe): one FULL default-dims 4-order precompute, every texel of every stage, "
+              f"{dt:.1f} s wall on {host_cores()} cores ({cpu_model()}); result sane: {ok}")
+    return dt * 1e3, sample
 
 
 def ncu_dram_traffic():
@@ -154,29 +148,30 @@ def host_cores() -> int:
 
 def run_reference(args, rank: int):
     """--impl reference: the reference's algorithm on the host cores.  The reference itself (Rust + GLSL on Vulkan)
-    cannot run here — no cargo, no shaderc, no Vulkan loader/ICD (lavapipe or NVIDIA) in the image — so this arm
-    times the oracle port, OpenMP over all host cores."""
+    cannot run here -- no cargo, no shaderc, no Vulkan loader/ICD (lavapipe or NVIDIA) in the image -- so this arm
+    times the oracle port, OpenMP over all host cores.  Every step is one FULL default-dims 4-order precompute (real
+    tables, every texel); as many of the requested steps run as fit in ~100 s, and `steps` reports what ran."""
     if rank != 0:
         return
-    total = args.steps + args.warmup
-    # calibrate on a thin sample (every 64th texel), then pick the texel stride that keeps the whole run near 100 s
-    # whatever the core count is
-    t0 = time.perf_counter()
-    cpu_precompute_ms(64)
-    full_s = max((time.perf_counter() - t0) * 64.0, 1.0)          # estimated cost of a pass over every texel
-    stride = max(1, math.ceil(total * full_s / 100.0))
-    vals, sample = [], ""
-    for i in range(total):
-        ms, sample = cpu_precompute_ms(stride)
-        if i >= args.warmup:
-            vals.append(ms)
+    budget_s = 100.0
+    t_start = time.perf_counter()
+    runs, sample = [], ""
+    while len(runs) < args.warmup + args.steps:
+        spent = time.perf_counter() - t_start
+        if runs and spent + spent / len(runs) > budget_s:      # the next pass would not fit; at least one always runs
+            break
+        ms, sample = cpu_precompute_ms()
+        runs.append(ms)
+    warm = min(args.warmup, len(runs) - 1)                      # warm-up passes first, but one timed pass is kept
+    vals = runs[warm:]
     v = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": warm, "requested": {"steps": args.steps, "warmup": args.warmup}, "ms_per_step": v,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores(), "cpu": cpu_model(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
             "reference_unavailable": "Rust+GLSL/Vulkan reference cannot be built or run in this image (no cargo, shaderc, "
                                      "Vulkan loader or ICD); lavapipe and B200-Vulkan baselines are unavailable"}
     print(json.dumps(line), flush=True)
@@ -275,13 +270,17 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     d2h = hT.numel() * 4 + hS.numel() * 2 + hE.numel() * 4
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- legs every rank takes part in: the 256-view sweep split over the ranks, the sharded high-resolution build ---
+    fma_tflops, sfu_gops = builder.measure_peaks() if rank == 0 else (None, None)
+    render = None if args.no_render else render_leg(args, builder, pending, stream, dev, rank, world, fma_tflops, sfu_gops)
+    del flush_buf
+    hires = None if args.no_hires else hires_leg(args, builder, rank, local_rank, world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- rank 0, N = 1 extras: roofline of the dominant kernel, render throughput, CPU baseline -----------------
-    fma_tflops, sfu_gops = builder.measure_peaks()
+    # ---- rank 0 extras: roofline of the dominant kernel, CPU baseline -------------------------------------------
     roof = {}
     for order in (2, 3):
         n = 10
@@ -313,12 +312,19 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                         "achieved_gbs": 3 * 8 * 32 * 128 * 256 / (dens_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_file) else "fallback"}}
 
-    render = render_leg(args, builder, pending, stream, dev, fma_tflops, sfu_gops) if world == 1 else None
+    # the unit that actually binds the kernel (ncu: l1tex__data_pipe_lsu_wavefronts 80-86 %): shared-memory words returned
+    # to the register file, 32 per SM and clock, 6 (12 at order 2) table words per sample
+    sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+    lds_peak = builder.sm_count() * 32 * sm_clk * 1e6
+    roofline["lds"] = {"words_per_sample": {"order2": 12, "order3": 6}, "peak_words_per_s": lds_peak,
+                       "frac": {"order2": DENSITY_SAMPLES * 12 / (roof[2] * 1e-3) / lds_peak,
+                                "order3": DENSITY_SAMPLES * 6 / (roof[3] * 1e-3) / lds_peak},
+                       "note": "table words only; shuffles, ground rows and the prologue share the same pipe"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sample = cpu_precompute_ms(2)
-        cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample}
+        v, sample = cpu_precompute_ms()
+        cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "cpu": cpu_model(), "kind": "port", "sample": sample}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -330,67 +336,99 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                     "note": "one graph replay that carries the precompute and the read-back of transmittance, scattering, irradiance into "
                             "pinned host memory (fb_pending_set_readback), host wall clock from submit to stream sync"},
             "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "render": render}
+            "cpu_baseline": cpu, "render": render, "hires": hires}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_hires(args, rank: int, local_rank: int, world: int):
-    """--workload hires: BASELINE.json configs[2] — scattering 128x512x128x32 (2 GiB per 3-D table), transmittance
-    1024x256, 8 orders, ONE atmosphere split into r-slabs across the ranks with NCCL all-gathers of the slabs
-    (fuzzyblue_b200/sharded.py).  Strong scaling: the job is fixed, `value` is the time of one whole precompute."""
+def hires_params(scale: int = 1):
+    import fuzzyblue_b200 as fb
+    return fb.Parameters(order=8, transmittance_mu_size=1024, transmittance_r_size=256, scattering_r_size=128 // scale,
+                         scattering_mu_size=512 // scale, scattering_mu_s_size=128 // scale, scattering_nu_size=32 // scale)
+
+
+def hires_leg(args, builder, rank: int, local_rank: int, world: int, dev):
+    """BASELINE.json configs[2] -- scattering 128x512x128x32 (2 GiB per 3-D table), transmittance 1024x256, 8 orders: ONE
+    atmosphere split into r-slabs across the ranks, built by fb_pending_run_sharded (fuzzyblue_b200/csrc/fb_sharded.cu):
+    per order one all-gather of scattering_density, one-slice halos of the previous order's table, the irradiance rows,
+    all over NCCL.  Strong scaling: the job is fixed, `value` is the device time of one whole precompute (max over ranks).
+    Returns the record on rank 0."""
     import torch
     import torch.distributed as dist
 
     import fuzzyblue_b200 as fb
     from fuzzyblue_b200 import sharded
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     scale = args.hires_scale          # 1 = the full config; 2 halves every scattering axis (1/16 of the work)
-    p = fb.Parameters(order=8, transmittance_mu_size=1024, transmittance_r_size=256, scattering_r_size=128 // scale,
-                      scattering_mu_size=512 // scale, scattering_mu_s_size=128 // scale, scattering_nu_size=32 // scale)
-    builder = fb.Builder(local_rank)
+    p = hires_params(scale)
+    flags = sharded.GATHER_RESULT | (sharded.NO_PIPELINE if args.hires_no_pipeline else 0)
     stream = torch.cuda.Stream(device=dev)
+    comm = sharded.NcclComm(local_rank, rank, world) if world > 1 else None
     pend = fb.Atmosphere.allocate(builder, p)
-    sp = sharded.ShardedPrecompute(sharded.PendingBackend(pend, stream), p.scattering_r_size, p.order, rank, world)
     sampler = ClockSampler(local_rank)
+    warm, steps = 1, max(1, args.hires_steps)
     times = []
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup + args.steps):
-            if i == args.warmup and rank == 0:
-                sampler.start()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            sp.run()
-            e1.record(stream)
-            stream.synchronize()
-            if i >= args.warmup:
-                times.append(e0.elapsed_time(e1))
+    for i in range(warm + steps):
+        if i == warm and rank == 0:
+            sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        pend.run_sharded(comm, rank, world, flags, stream)
+        e1.record(stream)
+        stream.synchronize()
+        if i >= warm:
+            times.append(e0.elapsed_time(e1))
+    launches = pend.launch_count()
+    slow = pend.slow_stages()
+    finite = bool(torch.isfinite(torch.from_numpy(pend.atmosphere().read_irradiance())).all())
     total = torch.tensor([sum(times)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
+    pend.close()
+    if comm is not None:
+        comm.close()
+    builder.trim()
+    if rank != 0:
+        return None
+    ms = float(total.item()) / steps
+    rx = sharded.bytes_received(p, min(1, world - 1), world, flags)
+    n_steps = len(sharded.plan(p, 0, world, flags))
+    return {"metric": "LUT precompute ms (8 orders, high-resolution dims)", "value": ms, "unit": "ms", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"default Earth physics, T 1024x256, S r{p.scattering_r_size} x mu{p.scattering_mu_size} x "
+                                   f"mu_s{p.scattering_mu_s_size} x nu{p.scattering_nu_size}, 8 orders, r-slab sharded "
+                                   f"(BASELINE.json configs[2], scale 1/{scale})",
+                       "inputs": "40 bytes of table per texel, far larger than L2", "kernels": "FAST",
+                       "entry_point": "fb_pending_run_sharded (C ABI, NCCL resolved at run time)"},
+            "collective": {"exchanges_per_step": rx["exchanges"], "plan_steps": n_steps,
+                           "bytes_received_per_rank_per_step": rx["total"], "all_gather_bytes": rx["all_gather"],
+                           "halo_bytes": rx["halo"], "irradiance_row_bytes": rx["rows"],
+                           "limiting": "the all-gather of scattering_density before each multiple_scattering pass "
+                                       "(7 of them + the final table: (N-1)/N x 2 GiB received per rank each)",
+                           "overlap": "none (whole-slab ncclAllGather)" if args.hires_no_pipeline else
+                                      "sub-slab exchanges on a communication stream behind the next sub-slab's density kernels"},
+            "clocks": clocks, "gpu_launches": launches * steps, "launches_per_step": launches, "slow_stages": slow,
+            "results_finite": finite}
+
+
+def run_hires(args, rank: int, local_rank: int, world: int):
+    """--workload hires: the `hires` leg alone, as the run's one JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    import fuzzyblue_b200 as fb
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.hires_steps = args.steps
+    line = hires_leg(args, fb.Builder(local_rank), rank, local_rank, world, dev)
     if rank == 0:
-        ms = float(total.item()) / args.steps
-        W, M, R = p.scattering_nu_size * p.scattering_mu_s_size, p.scattering_mu_size, p.scattering_r_size
-        gather_bytes = sp.bytes_received // (args.warmup + args.steps)
-        line = {"metric": "LUT precompute ms (8 orders, high-resolution dims)", "value": ms, "unit": "ms", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"default Earth physics, T 1024x256, S r{R} x mu{M} x mu_s{p.scattering_mu_s_size} x nu{p.scattering_nu_size}, "
-                                       f"8 orders, r-slab sharded (BASELINE.json configs[2], scale 1/{scale})",
-                           "inputs": "40 bytes of table per texel, far larger than L2", "kernels": "FAST"},
-                "collective": {"all_gathers_per_step": sp.gathers // (args.warmup + args.steps), "sub_slab_chunks": sp.chunks,
-                               "bytes_received_per_rank_per_step": gather_bytes,
-                               "overlap": "sub-slab all-gathers on a communication stream behind the next sub-slab's kernels"},
-                "clocks": clocks, "gpu_launches": pend.launch_count() * args.steps // (args.warmup + args.steps),
-                "launches_per_step": pend.launch_count() // (args.warmup + args.steps)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -486,16 +524,23 @@ def render_roofline(px: int, geometry_px: int, total_ms: float, fma_tflops, sfu_
             "tally": "as written, per pixel: geometry 430 flop + 39 SFU ops, sky 290 + 29 (SURVEY.md §8a a24)"}
 
 
-def render_leg(args, builder, pending, stream, dev, fma_tflops=None, sfu_gops=None):
+def render_leg(args, builder, pending, stream, dev, rank=0, world=1, fma_tflops=None, sfu_gops=None):
     """Second half of BASELINE.json's metric: sky evaluation at 3840x2160 over a 256-view camera sweep
-    (config[4]), in chunks of 8 views (depth + two RGBA32F outputs per chunk = 2.4 GB >> L2)."""
+    (config[4]), in chunks of 8 views (depth + two RGBA32F outputs per chunk = 2.4 GB >> L2).  At N > 1 rank r draws
+    the views r, r + N, r + 2N, ... from its own copy of the default-Earth tables (8.25 MiB, built per rank): no
+    collective on the data path; `value` = all 256 views' pixels / the slowest rank's device time."""
     import numpy as np
     import torch
+    import torch.distributed as dist
 
     import fuzzyblue_b200 as fb
     from fuzzyblue_b200 import synthetic
     W, H, VIEWS, CHUNK = 3840, 2160, args.render_views, 8
-    atm = pending.atmosphere()
+    own = None
+    if rank != 0:      # ranks > 0 hold a randomised atmosphere for the precompute leg: the sweep uses the default Earth
+        own = fb.Atmosphere.build(builder, stream, fb.Parameters())
+        stream.synchronize()
+    atm = (own or pending).atmosphere()
     renderer = fb.Renderer(builder)
     draws, extra = synthetic.camera_sweep(VIEWS, W, H)
     depth = torch.empty((CHUNK, H, W), device=dev)
@@ -521,22 +566,34 @@ def render_leg(args, builder, pending, stream, dev, fma_tflops=None, sfu_gops=No
         return torch.where(hit, 0.1 / z.clamp_min(1e-9), torch.zeros_like(z)).float()
 
     total_ms, px, n_launch, geometry_px = 0.0, 0, 0, 0
-    for c0 in range(0, VIEWS, CHUNK):
-        n = min(CHUNK, VIEWS - c0)
-        for j in range(n):
-            depth[j] = make_depth(c0 + j)
+    mine = list(range(rank, VIEWS, world))
+    for c0 in range(0, len(mine), CHUNK):
+        ks = mine[c0:c0 + CHUNK]
+        n = len(ks)
+        for j, k in enumerate(ks):
+            depth[j] = make_depth(k)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        chunk_draws = [draws[k] for k in ks]
         if c0 == 0:   # warm-up
-            renderer.draw_sweep(stream, atm, draws[c0:c0 + n], depth, color, transm, W, H)
+            renderer.draw_sweep(stream, atm, chunk_draws, depth, color, transm, W, H)
         e0.record(stream)
-        renderer.draw_sweep(stream, atm, draws[c0:c0 + n], depth, color, transm, W, H)
+        renderer.draw_sweep(stream, atm, chunk_draws, depth, color, transm, W, H)
         e1.record(stream)
         stream.synchronize()
         total_ms += e0.elapsed_time(e1)
         px += n * W * H
         n_launch += 1
         geometry_px += int((depth[:n] > 0).sum().item())      # finite-depth pixels take the two-look-up path
+    my_ms = total_ms
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([px, geometry_px, n_launch], device=dev, dtype=torch.int64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_ms, (px, geometry_px, n_launch) = float(t.item()), [int(v) for v in cnt.tolist()]
+    if rank != 0:
+        return None
     mpx = px / (total_ms * 1e-3) / 1e6
     # end to end for one 4K frame: depth from pinned host memory in, both RGBA32F outputs back to pinned host memory
     hd = depth[0].cpu().pin_memory()
@@ -559,10 +616,13 @@ def render_leg(args, builder, pending, stream, dev, fma_tflops=None, sfu_gops=No
         frame()
         times.append(time.perf_counter() - t0)
     e2e_s = sorted(times)[len(times) // 2]      # PCIe-bound (33 MB in, 265 MB out per frame): median of 9 frames
-    roofline = render_roofline(px, geometry_px, total_ms, fma_tflops, sfu_gops)
-    return {"metric": "sky evaluation Mpixel/s at 3840x2160", "value": mpx, "unit": "Mpixel/s", "views": VIEWS,
-            "ms_per_frame": total_ms / VIEWS, "gpu_launches": n_launch, "inputs": "depth + outputs per 8-view chunk 2.4 GB > L2",
-            "hbm": {"bytes_per_pixel": 36, "achieved_gbs": 36 * px / (total_ms * 1e-3) / 1e9},
+    # per-GPU roofline: this rank's pixels over this rank's time (the sweep's aggregate rate is `value`)
+    roofline = render_roofline(px // world, geometry_px // world, my_ms, fma_tflops, sfu_gops)
+    return {"metric": "sky evaluation Mpixel/s at 3840x2160", "value": mpx, "unit": "Mpixel/s", "views": VIEWS, "n_gpus": world,
+            "scaling": "strong", "sharding": "views rank::N, tables built per rank, no collective",
+            "ms_per_frame": total_ms * world / VIEWS, "ms_sweep": total_ms, "gpu_launches": n_launch,
+            "inputs": "depth + outputs per 8-view chunk 2.4 GB > L2",
+            "hbm": {"bytes_per_pixel": 36, "achieved_gbs_per_gpu": 36 * (px / world) / (my_ms * 1e-3) / 1e9},
             "roofline": roofline,
             "e2e": {"value": W * H / e2e_s / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4,
                     "d2h_bytes_per_step": W * H * 32}}
@@ -576,9 +636,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--render-views", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-hires", action="store_true")
+    ap.add_argument("--hires-steps", type=int, default=2)
     ap.add_argument("--workload", default="default", choices=["default", "hires", "batch"])
     ap.add_argument("--batch-atmospheres", type=int, default=1024)
     ap.add_argument("--hires-scale", type=int, default=1)
+    ap.add_argument("--hires-no-pipeline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -142,6 +142,16 @@ ABI = {
     "fb_external_semaphore_signal": (c_int, [c_void_p, c_uint64, c_void_p]),
     "fb_external_semaphore_wait": (c_int, [c_void_p, c_uint64, c_void_p]),
     "fb_external_semaphore_destroy": (None, [c_void_p]),
+    "fb_params_slow_stages": (c_uint32, [_P(FbParams)]),
+    "fb_pending_slow_stages": (c_uint32, [c_void_p]),
+    "fb_pending_wait": (c_int, [c_void_p]),
+    "fb_sharded_plan": (c_int, [_P(FbParams), c_uint32, c_int, c_int, c_uint32, c_void_p, c_uint32, _P(c_uint32)]),
+    "fb_atmosphere_build_sharded": (c_int, [c_void_p, _P(FbParams), c_uint32, c_void_p, c_int, c_int, c_uint32, c_void_p, _P(c_void_p)]),
+    "fb_pending_run_sharded": (c_int, [c_void_p, c_void_p, c_int, c_int, c_uint32, c_void_p]),
+    "fb_nccl_version": (c_int, [_P(c_int)]),
+    "fb_nccl_unique_id": (c_int, [c_void_p]),
+    "fb_nccl_comm_create": (c_int, [c_int, c_int, c_int, c_void_p, _P(c_void_p)]),
+    "fb_nccl_comm_destroy": (c_int, [c_void_p]),
 }
 
 _LIB = None
@@ -461,11 +471,29 @@ class PendingAtmosphere:
         _check(_lib().fb_pending_atmosphere(self._h, byref(h)))
         return Atmosphere(h, self._builder, owned=False)
 
-    def assert_ready(self, check: bool = True) -> Atmosphere:   # :2208-2211
+    def wait(self):
+        """Block until everything submitted through this object has finished (the fence wait of tests/smoke.rs:147-155)."""
+        _check(_lib().fb_pending_wait(self._h))
+
+    def assert_ready(self, check: bool = True, wait: bool = True) -> Atmosphere:   # :2208-2211
+        """Consumes the pending, frees the temporaries.  The reference leaves a too-early call undefined; here
+        ``wait=True`` (default) first waits for the precompute's own completion events, ``wait=False, check=True``
+        raises FuzzyblueError(FB_ERR_NOT_READY) if work is still in flight (the pending stays usable), and
+        ``check=False`` trusts the caller as the reference does."""
+        if wait and check:
+            self.wait()
         h = c_void_p()
         _check(_lib().fb_pending_assert_ready(self._h, 1 if check else 0, byref(h)))
         self._h = c_void_p()
         return Atmosphere(h, self._builder, owned=True)
+
+    def slow_stages(self) -> int:
+        """Bit s set: stage s ran the one-thread-per-texel transcription although FAST kernels were asked for."""
+        return int(_lib().fb_pending_slow_stages(self._h))
+
+    def run_sharded(self, comm, rank: int, world: int, flags: int = 0, stream=None):
+        """The r-slab sharded schedule (fb_sharded_plan) on the images this pending owns, exchanges over NCCL."""
+        _check(_lib().fb_pending_run_sharded(self._h, c_void_p(comm.handle if comm is not None else 0), rank, world, flags, _stream(stream)))
 
     def resubmit(self, stream=None):
         """Replay the recorded command stream (what benches/precompute.rs:138-148 times)."""
@@ -518,10 +546,13 @@ class PendingAtmosphere:
 
 
 def build_batch(builder: Builder, params: List[Parameters], stream=None) -> List[PendingAtmosphere]:
-    """Independent atmospheres (BASELINE.json config 4), overlapped on forked streams."""
+    """Independent atmospheres (BASELINE.json config 4), overlapped on forked streams.  The C entry point takes ONE
+    scattering order for the whole batch, so parameter sets of different orders are refused here."""
     n = len(params)
     if n == 0:
         return []
+    if any(p.order != params[0].order for p in params):
+        raise ValueError("build_batch: every atmosphere of a batch must use the same scattering order")
     raws = (FbParams * n)(*[p.raw() for p in params])
     outs = (c_void_p * n)()
     _check(_lib().fb_atmosphere_build_batch(builder._h, raws, n, params[0].order, _stream(stream), outs))

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -20,6 +21,7 @@
 #include <vector>
 
 #include "../../include/fuzzyblue.h"
+#include "fb_internal.h"
 #include "fb_kernels.h"
 
 using namespace fb;
@@ -36,20 +38,17 @@ static_assert(offsetof(FbDrawParams, sun_direction) == 80, "sun_direction after 
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
-static int fail(int status, const std::string& msg) {
+namespace fb {
+int fail(int status, const std::string& msg) {
     g_last_error = msg;
     return status;
 }
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
     (void)cudaGetLastError();   // clear the sticky-less error so later calls are not poisoned
     int st = (e == cudaErrorMemoryAllocation) ? FB_ERR_OUT_OF_MEMORY : FB_ERR_CUDA;
     return fail(st, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
-#define FB_CUDA(call)                                        \
-    do {                                                     \
-        cudaError_t e__ = (call);                            \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-    } while (0)
+}  // namespace fb
 
 const char* fb_status_string(int s) {
     switch (s) {
@@ -123,6 +122,22 @@ int fb_params_validate(const FbParams* p) {
     if (texels > ((int64_t)1 << 31)) return fail(FB_ERR_INVALID_ARGUMENT, "params: scattering table exceeds 2^31 texels");
     if (!(p->top_radius > p->bottom_radius) || !(p->bottom_radius > 0.f))
         return fail(FB_ERR_INVALID_ARGUMENT, "params: need 0 < bottom_radius < top_radius");
+    // The restructured kernels address shared-memory tables from geometry without per-sample clamps, which is safe for
+    // finite geometry only: a NaN / infinite scalar would become a wild address (a sticky device fault) where the
+    // reference merely writes NaN texels.  Reject such blocks up front.
+    const float* f = reinterpret_cast<const float*>(p);
+    for (int i = 0; i < 23; ++i)                                        // the 92 bytes of floats ahead of the sizes
+        if (!std::isfinite(f[i])) return fail(FB_ERR_INVALID_ARGUMENT, "params: non-finite value in the parameter block");
+    const FbDensityProfile* prof[3] = {&p->rayleigh_density, &p->mie_density, &p->absorption_density};
+    for (const FbDensityProfile* d : prof)
+        for (const FbDensityProfileLayer& l : d->layers)
+            if (!std::isfinite(l.width) || !std::isfinite(l.exp_term) || !std::isfinite(l.exp_scale) || !std::isfinite(l.linear_term) ||
+                !std::isfinite(l.constant_term))
+                return fail(FB_ERR_INVALID_ARGUMENT, "params: non-finite value in a density profile");
+    if (!(p->mu_s_min >= -1.f && p->mu_s_min <= 0.f))
+        return fail(FB_ERR_INVALID_ARGUMENT, "params: mu_s_min must lie in [-1, 0] (cosine of the largest sun zenith angle tabulated, scattering.h:50-56)");
+    if (!(p->mie_phase_function_g > -1.f && p->mie_phase_function_g < 1.f))
+        return fail(FB_ERR_INVALID_ARGUMENT, "params: mie_phase_function_g must lie in (-1, 1) (util.h:31-34)");
     return FB_OK;
 }
 int fb_params_transmittance_extent(const FbParams* p, FbExtent2D* o) {   // precompute.rs:772-777
@@ -144,60 +159,117 @@ int fb_params_scattering_extent(const FbParams* p, FbExtent3D* o) {      // :786
 // ---------------------------------------------------------------------------------------------
 // objects
 // ---------------------------------------------------------------------------------------------
-// Device blocks released by a finished precompute are kept (up to `limit` bytes) and handed to the next one of the
-// same dims: cudaMalloc / cudaFree cost ~0.2 ms each and cudaFree synchronises the whole device, which would serialise
-// a batch of independent atmospheres.  Shared by the builder and everything built from it, so an Atmosphere may
-// outlive its Builder (the reference holds an Arc<Builder> for the same reason, precompute.rs:1037).
-struct BlockCache {
-    int device;
-    size_t limit, cached;
-    std::mutex m;
-    std::multimap<size_t, void*> free_blocks;
-    explicit BlockCache(int dev) : device(dev), limit((size_t)8 << 30), cached(0) {}
-    cudaError_t get(void** p, size_t n) {
-        {
-            std::lock_guard<std::mutex> g(m);
-            auto it = free_blocks.find(n);
-            if (it != free_blocks.end()) {
-                *p = it->second;
-                free_blocks.erase(it);
-                cached -= n;
-                return cudaSuccess;
-            }
+// Completion and BlockCache (fb_internal.h): stream-ordered reuse of released device blocks.
+namespace fb {
+void Completion::note(cudaStream_t s) {
+    std::lock_guard<std::mutex> g(m);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess) { (void)cudaGetLastError(); unknown = true; return; }
+    if (cs != cudaStreamCaptureStatusNone) { unknown = true; return; }   // the caller records us into a graph of its own
+    for (auto& kv : ev)
+        if (kv.first == s) {
+            if (cudaEventRecord(kv.second, s) != cudaSuccess) { (void)cudaGetLastError(); unknown = true; }
+            return;
         }
-        cudaError_t e = cudaMalloc(p, n);
-        if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back to the driver and retry once
-            (void)cudaGetLastError();
-            trim();
-            e = cudaMalloc(p, n);
-        }
+    if (ev.size() >= 32) { unknown = true; return; }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, s) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (e) cudaEventDestroy(e);
+        unknown = true;
+        return;
+    }
+    ev.emplace_back(s, e);
+}
+cudaError_t Completion::query() {
+    std::lock_guard<std::mutex> g(m);
+    if (unknown) return cudaDeviceSynchronize();      // untracked work: the only safe answer is to drain the device
+    for (auto& kv : ev) {
+        const cudaError_t e = cudaEventQuery(kv.second);
+        if (e != cudaSuccess) return e;               // cudaErrorNotReady or a real error
+    }
+    return cudaSuccess;
+}
+cudaError_t Completion::wait() {
+    std::lock_guard<std::mutex> g(m);
+    if (unknown) {
+        const cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) unknown = false;
         return e;
     }
-    void put(void* p, size_t n) {
-        if (!p) return;
-        {
-            std::lock_guard<std::mutex> g(m);
-            if (cached + n <= limit) {
-                free_blocks.emplace(n, p);
-                cached += n;
-                return;
-            }
-        }
-        cudaFree(p);
+    for (auto& kv : ev) {
+        const cudaError_t e = cudaEventSynchronize(kv.second);
+        if (e != cudaSuccess) return e;
     }
-    void trim() {
+    return cudaSuccess;
+}
+cudaError_t Completion::stream_wait(cudaStream_t s) {
+    std::unique_lock<std::mutex> g(m);
+    if (unknown) { g.unlock(); return wait(); }
+    for (auto& kv : ev) {
+        if (kv.first == s) continue;                  // stream order already covers it
+        const cudaError_t e = cudaStreamWaitEvent(s, kv.second, 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+Completion::~Completion() {
+    for (auto& kv : ev) cudaEventDestroy(kv.second);
+}
+
+cudaError_t BlockCache::get(void** p, size_t n) {
+    Block blk{nullptr, nullptr};
+    {
         std::lock_guard<std::mutex> g(m);
-        for (auto& kv : free_blocks) cudaFree(kv.second);
-        free_blocks.clear();
-        cached = 0;
+        auto it = free_blocks.find(n);
+        if (it != free_blocks.end()) {
+            blk = it->second;
+            free_blocks.erase(it);
+            cached -= n;
+        }
     }
-    ~BlockCache() {
-        int prev = -1;
-        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device);
+    if (blk.p) {
+        // the previous owner's kernels may still be in flight on its streams: wait for exactly that work
+        if (blk.busy) {
+            const cudaError_t e = blk.busy->wait();
+            if (e != cudaSuccess) { cudaFree(blk.p); return e; }
+        }
+        *p = blk.p;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, n);
+    if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back to the driver and retry once
+        (void)cudaGetLastError();
         trim();
-        if (prev >= 0 && prev != device) cudaSetDevice(prev);
+        e = cudaMalloc(p, n);
     }
-};
+    return e;
+}
+void BlockCache::put(void* p, size_t n, const std::shared_ptr<Completion>& busy) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(m);
+        if (cached + n <= limit) {
+            free_blocks.emplace(n, Block{p, busy});
+            cached += n;
+            return;
+        }
+    }
+    cudaFree(p);                            // synchronises the device itself
+}
+void BlockCache::trim() {
+    std::lock_guard<std::mutex> g(m);
+    for (auto& kv : free_blocks) cudaFree(kv.second.p);
+    free_blocks.clear();
+    cached = 0;
+}
+BlockCache::~BlockCache() {
+    int prev = -1;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) cudaSetDevice(device);
+    trim();
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+}
+}  // namespace fb
 
 // ---------------------------------------------------------------------------------------------
 // Exportable device memory: the kept block as a CUDA virtual-memory allocation whose POSIX
@@ -284,55 +356,7 @@ static void vmm_free(void* p, unsigned long long handle, size_t alloc_bytes) {
     v.Release((CUmemGenericAllocationHandle)handle);
 }
 
-struct FbBuilder {
-    int device;
-    int sm_count;
-    int kernels;
-    int exportable;          // kept blocks come from the virtual-memory API as fd-exportable allocations
-    Trig trig;
-    std::shared_ptr<BlockCache> cache;
-};
-
-struct FbAtmosphere {
-    int device;
-    int kernels;
-    std::shared_ptr<BlockCache> cache;
-    void* block;             // one device block: [scattering | transmittance | irradiance]
-    size_t block_bytes;
-    bool vmm;                // block is an exportable virtual-memory allocation (not from the cache)
-    unsigned long long vmm_handle;
-    size_t vmm_bytes;        // allocation size (block_bytes rounded up to the granularity)
-    size_t off_transmittance, off_irradiance;
-    FbParams P;
-    float4* transmittance;
-    float4* irradiance;
-    uint2* scattering;
-    // identity of the table CONTENTS for a renderer's derived copy: `serial` is unique per atmosphere, `version` counts
-    // the submissions that (re)write the tables through the owning PendingAtmosphere
-    uint64_t serial, version;
-};
 static std::atomic<uint64_t> g_atmosphere_serial{1};
-
-struct FbPending {
-    FbBuilder* builder;
-    std::shared_ptr<BlockCache> cache;
-    void* temp_block;        // one device block for the five temporaries and the kernel scratch
-    size_t temp_bytes;
-    FbParams P;
-    uint32_t order;
-    Images img;
-    FbAtmosphere* inner;     // Option<Atmosphere>, precompute.rs:2114
-    cudaGraphExec_t graph;   // pre-recorded command stream, instantiated lazily
-    int launches;
-    cudaStream_t side;       // indirect_irradiance overlaps the density main kernel here (FAST family)
-    cudaEvent_t ev_fork, ev_join;
-    // fb_pending_set_readback: host destinations recorded into the command stream.  The last multiple-scattering
-    // pass runs as RB_SLABS r-slabs on streams of descending priority, each followed by the copy of its slab of
-    // `scattering`, so the 8 MiB read-back hides behind the remaining slabs' kernels.
-    void *rb_T, *rb_S, *rb_E;
-    cudaStream_t rb_stream[4];
-    cudaEvent_t rb_ev;
-};
 constexpr int RB_SLABS = 4;
 static int rb_slabs() {      // FUZZYBLUE_B200_RB_SLABS=1..4 overrides the slab count (tuning experiments)
     static const int n = [] {
@@ -355,27 +379,16 @@ struct FbRenderer {
     uint64_t expanded_serial, expanded_version;
     cudaEvent_t expanded_ready;
     bool no_expand;              // FUZZYBLUE_B200_RENDER_FP16_TABLE set at creation: always tap the fp16 table (A/B tests)
+    std::shared_ptr<Completion> draws;   // every draw issued through this renderer, per stream: what a table rebuild waits for
 };
 constexpr size_t EXPANDED_MAX_BYTES = (size_t)256 << 20;
-
-struct DeviceGuard {
-    int prev;
-    bool ok;
-    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
-        if (cudaGetDevice(&prev) != cudaSuccess) return;
-        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-    }
-};
 
 static size_t bytes2d(int w, int h) { return (size_t)w * h * sizeof(float4); }
 static size_t bytes3d(const FbParams& P) {
     return (size_t)P.scattering_nu_size * P.scattering_mu_s_size * P.scattering_mu_size * P.scattering_r_size * sizeof(uint2);
 }
-static size_t image_bytes(const FbParams& P, int image) {
+namespace fb {
+size_t image_bytes(const FbParams& P, int image) {
     switch (image) {
         case FB_IMAGE_TRANSMITTANCE: return bytes2d(P.transmittance_mu_size, P.transmittance_r_size);
         case FB_IMAGE_IRRADIANCE:
@@ -388,7 +401,7 @@ static size_t image_bytes(const FbParams& P, int image) {
         default: return 0;
     }
 }
-static void* image_ptr(FbPending* p, int image) {
+void* image_ptr(FbPending* p, int image) {
     switch (image) {
         case FB_IMAGE_TRANSMITTANCE: return p->img.transmittance;
         case FB_IMAGE_IRRADIANCE: return p->img.irradiance;
@@ -401,6 +414,7 @@ static void* image_ptr(FbPending* p, int image) {
         default: return nullptr;
     }
 }
+}  // namespace fb
 
 int fb_builder_create(int device, FbBuilder** out) {
     if (!out) return fail(FB_ERR_INVALID_ARGUMENT, "fb_builder_create: NULL out");
@@ -544,7 +558,12 @@ int fb_builder_device(const FbBuilder* b) { return b ? b->device : -1; }
 int fb_builder_sm_count(const FbBuilder* b) { return b ? b->sm_count : 0; }
 
 static void free_pending_temps(FbPending* p) {
-    p->cache->put(p->temp_block, p->temp_bytes);
+    // work enqueued on the internal streams always joins the caller's stream before a submission returns, but an
+    // enqueue that failed half-way may have left some behind: make them part of what the block's next owner waits for
+    if (p->side) p->done->note(p->side);
+    for (cudaStream_t q : p->rb_stream) if (q) p->done->note(q);
+    if (p->comm) p->done->note(p->comm);
+    p->cache->put(p->temp_block, p->temp_bytes, p->done);
     p->temp_block = nullptr;
     p->img.delta_irradiance = nullptr;
     p->img.delta_rayleigh = p->img.delta_mie = p->img.scattering_density = p->img.delta_multiple_scattering = nullptr;
@@ -555,19 +574,21 @@ static void free_pending_temps(FbPending* p) {
     if (p->ev_join) { cudaEventDestroy(p->ev_join); p->ev_join = nullptr; }
     for (cudaStream_t& q : p->rb_stream) if (q) { cudaStreamDestroy(q); q = nullptr; }
     if (p->rb_ev) { cudaEventDestroy(p->rb_ev); p->rb_ev = nullptr; }
+    if (p->comm) { cudaStreamDestroy(p->comm); p->comm = nullptr; }
+    if (p->ev_comm) { cudaEventDestroy(p->ev_comm); p->ev_comm = nullptr; }
 }
 
 void fb_atmosphere_destroy(FbAtmosphere* a) {   // Drop, precompute.rs:1045-1073
     if (!a) return;
     DeviceGuard g(a->device);
     if (a->vmm) vmm_free(a->block, a->vmm_handle, a->vmm_bytes);
-    else a->cache->put(a->block, a->block_bytes);
+    else a->cache->put(a->block, a->block_bytes, a->done);   // draws / reads still in flight: the next owner waits for them
     delete a;
 }
 
 void fb_pending_destroy(FbPending* p) {         // Drop, precompute.rs:2122-2140
     if (!p) return;
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     free_pending_temps(p);
     if (p->inner) fb_atmosphere_destroy(p->inner);
     delete p;
@@ -585,7 +606,11 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     FbAtmosphere* a = new (std::nothrow) FbAtmosphere();
     if (!p || !a) { delete p; delete a; return fail(FB_ERR_OUT_OF_MEMORY, "host allocation"); }
     std::memset(&p->img, 0, sizeof p->img);
-    p->builder = b;
+    p->device = b->device; p->kernels = b->kernels; p->sm_count = b->sm_count; p->trig = b->trig;
+    p->done = std::make_shared<Completion>();
+    a->done = p->done;
+    p->slow_stages = 0;
+    p->comm = nullptr; p->ev_comm = nullptr;
     p->cache = b->cache;
     a->cache = b->cache;
     p->P = *params;
@@ -648,18 +673,23 @@ int fb_atmosphere_allocate(FbBuilder* b, const FbParams* params, uint32_t order,
     return FB_OK;
 }
 
-static LaunchCtx make_ctx(FbPending* p, cudaStream_t s) {
+namespace fb {
+LaunchCtx make_ctx(FbPending* p, cudaStream_t s) {
     LaunchCtx c;
     c.P = p->P;
-    c.trig = p->builder->trig;
+    c.trig = p->trig;
     c.img = p->img;
-    c.sm_count = p->builder->sm_count;
+    c.sm_count = p->sm_count;
     c.stream = s;
     return c;
 }
 
-static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order, int r0, int r1, int* launches) {
-    const bool fastk = p->builder->kernels == FB_KERNELS_FAST;
+int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order, int r0, int r1, int* launches) {
+    const bool fastk = p->kernels == FB_KERNELS_FAST;
+    if (fastk) {   // a stage these dims push onto the transcription kernels: remember it (fb_pending_slow_stages)
+        if (stage == FB_STAGE_SCATTERING_DENSITY && (!fast::density_is_fast(c.P) || !c.img.scratch)) p->slow_stages |= 1u << stage;
+        if (stage == FB_STAGE_MULTIPLE_SCATTERING && !fast::multiple_is_fast(c.P)) p->slow_stages |= 1u << stage;
+    }
     // a launch reports errors through cudaGetLastError(): make sure an error some earlier, unrelated runtime call in
     // this thread left behind is not attributed to this stage
     (void)cudaGetLastError();
@@ -675,7 +705,8 @@ static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order
             break;
         case FB_STAGE_INDIRECT_IRRADIANCE:
             if (order < 1) return fail(FB_ERR_INVALID_ARGUMENT, "indirect_irradiance needs order >= 1 (indirect_irradiance.comp:18)");
-            e = fastk ? fast::indirect_irradiance(c, (int)order) : ref::indirect_irradiance(c, (int)order);
+            if (r1 <= r0 || r1 > c.P.irradiance_r_size) return fail(FB_ERR_INVALID_ARGUMENT, "indirect_irradiance: bad row range");
+            e = fastk ? fast::indirect_irradiance(c, (int)order, r0, r1) : ref::indirect_irradiance(c, (int)order, r0, r1);
             break;
         case FB_STAGE_MULTIPLE_SCATTERING: e = fastk ? fast::multiple_scattering(c, r0, r1) : ref::multiple_scattering(c, r0, r1); break;
         case FB_STAGE_CLEAR_IRRADIANCE:
@@ -688,15 +719,16 @@ static int run_stage(FbPending* p, const LaunchCtx& c, int stage, uint32_t order
     if (launches) *launches += n;
     return FB_OK;
 }
+}  // namespace fb
 
 // The recorded command stream, src/precompute.rs:1671-2048.  Stream order replaces the pipeline
 // barriers; the parameter block travels as a kernel argument instead of vkCmdUpdateBuffer.
 static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
     if (p->inner) ++p->inner->version;
     LaunchCtx c = make_ctx(p, s);
-    const int R = p->P.scattering_r_size;
+    const int R = p->P.scattering_r_size, ER = p->P.irradiance_r_size;
     int st;
-    const bool fastk = p->builder->kernels == FB_KERNELS_FAST;
+    const bool fastk = p->kernels == FB_KERNELS_FAST;
     const bool overlap = fastk && p->order >= 2;
     const bool rb = p->rb_T || p->rb_S || p->rb_E;
     if ((overlap || rb) && !p->side) {
@@ -754,12 +786,13 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
         const bool last = order == p->order;
         if (!overlap) {
             STAGE(FB_STAGE_SCATTERING_DENSITY, order);           // :1878-1904, push constant `order`
-            STAGE(FB_STAGE_INDIRECT_IRRADIANCE, order - 1);      // :1927-1953, push constant `order - 1`
+            if ((st = run_stage(p, c, FB_STAGE_INDIRECT_IRRADIANCE, order - 1, 0, ER, launches)) != FB_OK) return st;   // :1927-1953, push constant `order - 1`
             if (last) COPY_OUT(s, p->rb_E, p->img.irradiance, bE);
         } else {
             // K4 reads delta_irradiance (row 0) only in its preparation kernel, K5 overwrites that image and reads
             // nothing K4 writes: K5 runs on a side stream next to K4's main kernel and joins before K6 (which
             // overwrites the delta_multiple_scattering K5 reads).
+            if (!fast::density_is_fast(c.P) || !c.img.scratch) p->slow_stages |= 1u << FB_STAGE_SCATTERING_DENSITY;
             cudaError_t e = fast::scattering_density(c, (int)order, 0, R, p->ev_fork);
             if (e != cudaSuccess) return cuda_fail(e, "scattering_density launch");
             if (launches) *launches += fast::launches_per_stage(c.P, FB_STAGE_SCATTERING_DENSITY, R);
@@ -767,7 +800,7 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
             side_used = true;
             LaunchCtx cs = c;
             cs.stream = p->side;
-            if ((st = run_stage(p, cs, FB_STAGE_INDIRECT_IRRADIANCE, order - 1, 0, R, launches)) != FB_OK) return st;
+            if ((st = run_stage(p, cs, FB_STAGE_INDIRECT_IRRADIANCE, order - 1, 0, ER, launches)) != FB_OK) return st;
             FB_CUDA(cudaEventRecord(p->ev_join, p->side));
             FB_CUDA(cudaStreamWaitEvent(s, p->ev_join, 0));
             if (last) COPY_OUT(p->side, p->rb_E, p->img.irradiance, bE);   // after the join point: K6 does not wait for it
@@ -812,7 +845,7 @@ static int enqueue_all(FbPending* p, cudaStream_t s, int* launches) {
 
 int fb_pending_set_readback(FbPending* p, void* host_transmittance, void* host_scattering, void* host_irradiance) {
     if (!p || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_set_readback: NULL / already taken");
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     p->rb_T = host_transmittance; p->rb_S = host_scattering; p->rb_E = host_irradiance;
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }   // re-recorded by the next resubmit
     return FB_OK;
@@ -825,13 +858,14 @@ int fb_atmosphere_build(FbBuilder* b, const FbParams* params, uint32_t order, vo
     int launches = 0;
     st = enqueue_all(*out, (cudaStream_t)stream, &launches);
     (*out)->launches = launches;
+    (*out)->done->note((cudaStream_t)stream);   // also after a failed enqueue: earlier stages are in flight on the blocks
     if (st != FB_OK) { fb_pending_destroy(*out); *out = nullptr; }
     return st;
 }
 
 int fb_pending_resubmit(FbPending* p, void* stream) {
     if (!p || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_resubmit: NULL / already taken");
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     if (!p->graph) {
         cudaStream_t cap;
         FB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -850,22 +884,33 @@ int fb_pending_resubmit(FbPending* p, void* stream) {
     }
     ++p->inner->version;
     FB_CUDA(cudaGraphLaunch(p->graph, (cudaStream_t)stream));
+    p->done->note((cudaStream_t)stream);
     return FB_OK;
 }
 int fb_pending_launch_count(const FbPending* p) { return p ? p->launches : 0; }
 
 int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_begin, uint32_t r_end, void* stream) {
     if (!p) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_run_stage: NULL");
-    const uint32_t R = (uint32_t)p->P.scattering_r_size;
+    // the slab counts altitude levels of the scattering table, or rows of the irradiance table for indirect_irradiance
+    const uint32_t R = (uint32_t)(stage == FB_STAGE_INDIRECT_IRRADIANCE ? p->P.irradiance_r_size : p->P.scattering_r_size);
     if (r_end == 0) r_end = R;
     if (r_begin >= r_end || r_end > R) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_run_stage: bad r slab");
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     LaunchCtx c = make_ctx(p, (cudaStream_t)stream);
     int n = 0;
     if (p->inner) ++p->inner->version;
     const int st = run_stage(p, c, stage, order, (int)r_begin, (int)r_end, &n);
     p->launches += n;   // stage-driven pendings accumulate; build / resubmit overwrite with the per-submit count
+    p->done->note((cudaStream_t)stream);
     return st;
+}
+uint32_t fb_pending_slow_stages(const FbPending* p) { return p ? p->slow_stages : 0; }
+uint32_t fb_params_slow_stages(const FbParams* p) {
+    if (!p) return 0;
+    uint32_t m = 0;
+    if (!fast::density_is_fast(*p)) m |= 1u << FB_STAGE_SCATTERING_DENSITY;
+    if (!fast::multiple_is_fast(*p)) m |= 1u << FB_STAGE_MULTIPLE_SCATTERING;
+    return m;
 }
 
 int fb_pending_image(FbPending* p, int image, void** dev_ptr, size_t* bytes) {
@@ -877,16 +922,18 @@ int fb_pending_image(FbPending* p, int image, void** dev_ptr, size_t* bytes) {
 int fb_pending_upload(FbPending* p, int image, const void* host, size_t bytes, void* stream) {
     if (!p || !host || image < 0 || image >= FB_IMAGE_COUNT) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_upload");
     if (bytes != image_bytes(p->P, image)) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_upload: size mismatch");
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     if (p->inner) ++p->inner->version;
     FB_CUDA(cudaMemcpyAsync(image_ptr(p, image), host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    p->done->note((cudaStream_t)stream);
     return FB_OK;
 }
 int fb_pending_download(FbPending* p, int image, void* host, size_t bytes, void* stream) {
     if (!p || !host || image < 0 || image >= FB_IMAGE_COUNT) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_download");
     if (bytes != image_bytes(p->P, image)) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_download: size mismatch");
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     FB_CUDA(cudaMemcpyAsync(host, image_ptr(p, image), bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    p->done->note((cudaStream_t)stream);
     return FB_OK;
 }
 
@@ -895,15 +942,27 @@ int fb_pending_atmosphere(FbPending* p, const FbAtmosphere** out) {
     *out = p->inner;
     return FB_OK;
 }
+int fb_pending_wait(FbPending* p) {
+    if (!p) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_wait: NULL");
+    DeviceGuard g(p->device);
+    const cudaError_t e = p->done->wait();
+    return e == cudaSuccess ? FB_OK : cuda_fail(e, "waiting for the precompute");
+}
 int fb_pending_assert_ready(FbPending* p, int check, FbAtmosphere** out) {
     if (!p || !out || !p->inner) return fail(FB_ERR_INVALID_ARGUMENT, "fb_pending_assert_ready");
-    DeviceGuard g(p->builder->device);
+    DeviceGuard g(p->device);
     if (check) {
-        // cudaFree below synchronises the device anyway; the check only turns a too-early call
-        // (which in the reference is undefined behaviour) into an error code.
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+        // Every submission left an event behind on its stream: a too-early call (undefined behaviour in the reference,
+        // precompute.rs:2208-2211) is an error code here, found without synchronising anything.  `p` stays valid.
+        const cudaError_t e = p->done->query();
+        if (e == cudaErrorNotReady) {
+            (void)cudaGetLastError();
+            return fail(FB_ERR_NOT_READY, "fb_pending_assert_ready: the precompute has not finished on its stream(s)");
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "querying the precompute's completion events");
     }
+    // check = 0: the temporaries go back to the block cache carrying the completion events, so their next owner waits
+    // for whatever is still in flight (stream-ordered reuse, fb_internal.h)
     *out = p->inner;
     p->inner = nullptr;
     fb_pending_destroy(p);
@@ -938,6 +997,7 @@ static int read_back(const FbAtmosphere* a, const void* src, size_t want, void* 
     if (bytes != want) return fail(FB_ERR_INVALID_ARGUMENT, "read: size mismatch");
     DeviceGuard g(a->device);
     FB_CUDA(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    a->done->note((cudaStream_t)stream);
     return FB_OK;
 }
 int fb_atmosphere_read_transmittance(const FbAtmosphere* a, void* host, size_t bytes, void* stream) {
@@ -965,6 +1025,7 @@ int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, void* T,
         pend->rb_T = T; pend->rb_S = S; pend->rb_E = E;
         int launches = 0;
         st = enqueue_all(pend, s, &launches);
+        pend->done->note(s);
         cudaError_t e = cudaStreamSynchronize(s);
         if (st == FB_OK && e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize");
         fb_pending_destroy(pend);
@@ -995,6 +1056,7 @@ int fb_atmosphere_build_batch(FbBuilder* b, const FbParams* params, uint32_t n, 
             int launches = 0;
             st = enqueue_all(out[i], side[i % lanes], &launches);
             out[i]->launches = launches;
+            out[i]->done->note(side[i % lanes]);   // also after a failed enqueue: its earlier stages are in flight
         }
         for (uint32_t l = 0; l < lanes && e == cudaSuccess; ++l) {
             cudaEvent_t join;
@@ -1025,6 +1087,7 @@ int fb_renderer_create(FbBuilder* b, FbRenderer** out) {
     r->sweep_capacity = 0;
     r->expanded = nullptr; r->expanded_bytes = 0; r->expanded_serial = 0; r->expanded_version = 0; r->expanded_ready = nullptr;
     r->no_expand = std::getenv("FUZZYBLUE_B200_RENDER_FP16_TABLE") != nullptr;
+    r->draws = std::make_shared<Completion>();
     *out = r;
     return FB_OK;
 }
@@ -1066,9 +1129,9 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
         }
         if (!r->expanded_ready) FB_CUDA(cudaEventCreateWithFlags(&r->expanded_ready, cudaEventDisableTiming));
         if (r->expanded_serial != a->serial || r->expanded_version != a->version) {
-            // earlier draws (any stream) may still read the old contents: they were ordered before `expanded_ready`'s
-            // last record only on their own streams, so drain them before overwriting
-            if (r->expanded_serial) FB_CUDA(cudaDeviceSynchronize());
+            // earlier draws (any stream) may still read the old contents: the rebuild waits, on the device, for the
+            // completion event each of those streams carries -- no host or device-wide synchronisation inside a draw
+            if (r->expanded_serial) FB_CUDA(r->draws->stream_wait((cudaStream_t)stream));
             cudaError_t ee = render_expand_scattering(a->P, a->transmittance, a->scattering, r->expanded, (cudaStream_t)stream);
             if (ee != cudaSuccess) return cuda_fail(ee, "render_expand_scattering launch");
             FB_CUDA(cudaEventRecord(r->expanded_ready, (cudaStream_t)stream));
@@ -1081,6 +1144,8 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
     cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, expanded, d, views > 1 ? r->sweep_draws : nullptr, views, depth,
                                (float4*)color, (float4*)transm, (float4*)blend, w, h, r->kernels, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_sky launch");
+    r->draws->note((cudaStream_t)stream);
+    a->done->note((cudaStream_t)stream);   // the tables must outlive this draw: their block's next owner waits for it
     return FB_OK;
 }
 
@@ -1128,6 +1193,7 @@ int fb_sky_radiance(const FbAtmosphere* a, const float* camera, const float* vie
     DeviceGuard g(a->device);
     cudaError_t e = sky_radiance(a->P, a->transmittance, a->scattering, camera, view_ray, sun_direction, n, radiance_out,
                                  transmittance_out, (cudaStream_t)stream);
+    a->done->note((cudaStream_t)stream);
     return e == cudaSuccess ? FB_OK : cuda_fail(e, "sky_radiance launch");
 }
 int fb_sun_and_sky_irradiance(const FbAtmosphere* a, const float* point, const float* normal, const float* sun_direction,
@@ -1137,5 +1203,6 @@ int fb_sun_and_sky_irradiance(const FbAtmosphere* a, const float* point, const f
     DeviceGuard g(a->device);
     cudaError_t e = sun_sky_irradiance(a->P, a->transmittance, a->irradiance, point, normal, sun_direction, n, sun_out, sky_out,
                                        (cudaStream_t)stream);
+    a->done->note((cudaStream_t)stream);
     return e == cudaSuccess ? FB_OK : cuda_fail(e, "sun_sky_irradiance launch");
 }

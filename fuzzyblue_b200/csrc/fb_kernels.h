@@ -46,7 +46,7 @@ cudaError_t transmittance(const LaunchCtx& c);
 cudaError_t direct_irradiance(const LaunchCtx& c);
 cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1);
 cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1);
-cudaError_t indirect_irradiance(const LaunchCtx& c, int order);
+cudaError_t indirect_irradiance(const LaunchCtx& c, int order, int row0, int row1);   // rows [row0, row1) of the irradiance table
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1);
 }  // namespace ref
 
@@ -58,8 +58,11 @@ cudaError_t direct_irradiance(const LaunchCtx& c);
 cudaError_t single_scattering(const LaunchCtx& c, int r0, int r1);
 // `after_prep` (optional) is recorded on c.stream once the stage no longer reads delta_irradiance
 cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cudaEvent_t after_prep = nullptr);
-cudaError_t indirect_irradiance(const LaunchCtx& c, int order);
+cudaError_t indirect_irradiance(const LaunchCtx& c, int order, int row0, int row1);
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1);
+// false when a stage of these dims runs the one-thread-per-texel transcription instead (a ~30x cliff the API reports)
+bool density_is_fast(const FbParams& P);
+bool multiple_is_fast(const FbParams& P);
 int launches_per_stage(const FbParams& P, int stage, int r_count);   // kernels one stage launches over r_count altitude levels
 }  // namespace fast
 

@@ -109,18 +109,23 @@ template <bool ORDER2> struct DensityCfg {
     static constexpr int NWARPS = 8;
 };
 struct DensityDims {
-    int nu, ms_tile, tiles, ms_shift;   // ms_tile = 1 << ms_shift (nu and the CTA's texel count are powers of two)
+    int nu, ms_tile, tiles, ms_shift;   // ms_tile = T / nu mu_s columns per CTA; ms_shift = log2(ms_tile), or -1 when it is not a power of two
 };
-static inline bool density_supported(const FbParams& P) {
+// what the restructured density kernels cover: a CTA needs at least one whole mu_s column (nu <= 128 texels at order 2) and
+// the eight ground rows must fit beside the table slice.  Anything else runs the one-thread-per-texel transcription, ~30x
+// slower -- reported through fb_params_slow_stages / fb_pending_slow_stages, never silently.
+bool density_is_fast(const FbParams& P) {
     const int nu = P.scattering_nu_size;
-    return nu >= 2 && nu <= 128 && (nu & (nu - 1)) == 0 && P.irradiance_mu_s_size <= 512;
+    return nu >= 2 && nu <= 128 && P.irradiance_mu_s_size <= 512;
 }
+static inline bool density_supported(const FbParams& P) { return density_is_fast(P); }
 static inline DensityDims density_dims(const FbParams& P, int T) {
     DensityDims d;
     d.nu = P.scattering_nu_size;
     d.ms_tile = T / d.nu;
     d.ms_shift = 0;
     while ((1 << d.ms_shift) < d.ms_tile) ++d.ms_shift;
+    if ((1 << d.ms_shift) != d.ms_tile) d.ms_shift = -1;   // nu = 3, 6, 12 ...: texel <-> (nu slice, mu_s column) by division
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
     return d;
 }
@@ -303,9 +308,9 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     F r, mu;
     {
         const int t = tid < TT ? tid : 0;
-        const int nui = t >> dd.ms_shift, msl = t & (dd.ms_tile - 1);
+        const int nui = dd.ms_shift >= 0 ? t >> dd.ms_shift : t / dd.ms_tile, msl = t - nui * dd.ms_tile;
         const int ms = tile * dd.ms_tile + msl;
-        const bool valid = tid < TT && ms < P.scattering_mu_s_size;
+        const bool valid = tid < TT && nui < dd.nu && ms < P.scattering_mu_s_size;   // nui >= nu: padding of a tile with T % nu != 0
         F mu_s, nu;
         bool hu;
         a.TexelToRMuMuSNu(valid ? (unsigned)(nui * P.scattering_mu_s_size + ms) : 0u, (unsigned)y, (unsigned)z, r, mu, mu_s, nu, hu);
@@ -443,7 +448,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     auto store = [&](int rec, float ar, float ag, float ab) {                 // the texel and its followers
         const uint2 v = pack_half4(ar, ag, ab, 0.f);
         const int t = (rec >> 14) & 0xff;
-        uint2* o = out + (out_row + (t >> dd.ms_shift) * P.scattering_mu_s_size + tile * dd.ms_tile + (t & (dd.ms_tile - 1)));
+        const int tn = dd.ms_shift >= 0 ? t >> dd.ms_shift : t / dd.ms_tile;
+        uint2* o = out + (out_row + tn * P.scattering_mu_s_size + tile * dd.ms_tile + (t - tn * dd.ms_tile));
 #pragma unroll 1
         for (int nf = rec >> 22; nf >= 0; --nf, o += P.scattering_mu_s_size) *o = v;   // followers: the next nu slices
     };
@@ -777,11 +783,11 @@ cudaError_t direct_irradiance(const LaunchCtx& c) { return ref::direct_irradianc
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_indirect_irradiance(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg,
                                                              Tex3 dR, Tex3 dM, Tex3 dMS, int order, float4* __restrict__ dE,
-                                                             float4* __restrict__ E) {
+                                                             float4* __restrict__ E, int texel0) {
     // one CTA (4 warps) per texel: thread t takes phi sample (t & 63) of the theta rows j = (t >> 6), +2, +4, ...
     __shared__ float part[4][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int texel = blockIdx.x;
+    const int texel = texel0 + blockIdx.x;
     const int W = P.irradiance_mu_s_size;
     const int x = texel % W, y = texel / W;
     A<F> a(P);
@@ -818,11 +824,11 @@ __global__ void __launch_bounds__(128) k_indirect_irradiance(const __grid_consta
     }
 }
 
-cudaError_t indirect_irradiance(const LaunchCtx& c, int order) {
-    const int texels = c.P.irradiance_mu_s_size * c.P.irradiance_r_size;
+cudaError_t indirect_irradiance(const LaunchCtx& c, int order, int row0, int row1) {   // rows [row0, row1) of the irradiance table
+    const int texels = c.P.irradiance_mu_s_size * (row1 - row0);
     k_indirect_irradiance<<<texels, 128, 0, c.stream>>>(c.P, c.trig, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie),
                                                         texS(c, c.img.delta_multiple_scattering), order,
-                                                        c.img.delta_irradiance, c.img.irradiance);
+                                                        c.img.delta_irradiance, c.img.irradiance, row0 * c.P.irradiance_mu_s_size);
     return cudaGetLastError();
 }
 
@@ -1251,16 +1257,26 @@ static cudaError_t multiple_launch(const LaunchCtx& c, int nt, int CH, size_t sm
     return cudaGetLastError();
 }
 
+// what the row-shared multiple-scattering kernel covers: a (nu, mu_s) row of at most 8192 texels whose staging slab fits
+// in shared memory (W = 8192: 17 KiB of node records + 128 KiB of slab).  Wider rows run the transcription (reported
+// through fb_params_slow_stages / fb_pending_slow_stages).
+bool multiple_is_fast(const FbParams& P) {
+    const int W = P.scattering_nu_size * P.scattering_mu_s_size;
+    if (W > 8192 || P.scattering_mu_s_size < 2) return false;
+    int CH = 3072 / W;
+    CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
+    return sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4) <= 200 * 1024;
+}
+
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     const int W = c.P.scattering_nu_size * c.P.scattering_mu_s_size;
-    if (W > 8192 || c.P.scattering_mu_s_size < 2) return ref::multiple_scattering(c, r0, r1);
+    if (!multiple_is_fast(c.P)) return ref::multiple_scattering(c, r0, r1);
     // default dims: 256 threads, 1 texel each; larger rows: up to 1024 threads x {1, 2, 4, 8} texels
     const int nt = W <= 1024 ? ((W + 31) / 32) * 32 : 1024;
     const int tpt = (W + nt - 1) / nt;
     int CH = 3072 / W;                            // nodes staged per pass: slab = CH * W * 16 B <= 48 KiB (64 KiB for W = 4096)
     CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
     const size_t smem = sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4);
-    if (smem > 200 * 1024) return ref::multiple_scattering(c, r0, r1);
     if (nt <= 256) return multiple_launch<1, 256>(c, nt, CH, smem, r0, r1);
     if (tpt == 1) return multiple_launch<1, 1024>(c, nt, CH, smem, r0, r1);
     if (tpt == 2) return multiple_launch<2, 1024>(c, nt, CH, smem, r0, r1);

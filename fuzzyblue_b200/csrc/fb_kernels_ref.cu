@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(128) k_scattering_density(const __grid_constan
 // ---- indirect_irradiance.comp ----------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_indirect_irradiance(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg,
                                                             Tex3 dR, Tex3 dM, Tex3 dMS, int order, float4* __restrict__ dE,
-                                                            float4* __restrict__ E) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+                                                            float4* __restrict__ E, int row0) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = row0 + blockIdx.y;
     if (x >= P.irradiance_mu_s_size || y >= P.irradiance_r_size) return;
     A<F> a(P);
     F r, mu_s;
@@ -261,11 +261,11 @@ cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1) {
         tex2(c.img.delta_irradiance, c.P.irradiance_mu_s_size, c.P.irradiance_r_size), order, c.img.scattering_density, r0);
     return cudaGetLastError();
 }
-cudaError_t indirect_irradiance(const LaunchCtx& c, int order) {
-    dim3 g((c.P.irradiance_mu_s_size + 31) / 32, c.P.irradiance_r_size);
+cudaError_t indirect_irradiance(const LaunchCtx& c, int order, int row0, int row1) {
+    dim3 g((c.P.irradiance_mu_s_size + 31) / 32, row1 - row0);
     k_indirect_irradiance<<<g, 32, 0, c.stream>>>(c.P, c.trig, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie),
                                                   texS(c, c.img.delta_multiple_scattering), order, c.img.delta_irradiance,
-                                                  c.img.irradiance);
+                                                  c.img.irradiance, row0);
     return cudaGetLastError();
 }
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {

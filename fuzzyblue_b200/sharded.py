@@ -1,27 +1,36 @@
 """r-slab sharding of ONE atmosphere across ranks (BASELINE.json config 3), one process per GPU.
 
-Which stage needs which exchange (dependency analysis of the shaders):
-  transmittance, direct/indirect irradiance   tiny 2-D tables: computed replicated on every rank
-  single_scattering                           r-local (needs only the transmittance table)
-  scattering_density at r                     reads the previous order's 3-D tables at the SAME r +- one slice (u_r lands
-                                              within 1e-2 texels of the texel centre) and row 0 of delta_irradiance
-  multiple_scattering at r                    marches along the ray through ALL r of scattering_density
-                                              (multiple_scattering.comp:35-44)  ->  all-gather before K6
-  indirect_irradiance                         rows are linear in r, unrelated to the scattering r grid -> needs ALL r of
-                                              the previous order's tables
-
-A slab [r0, r1) is one contiguous byte range of the linear [r][mu][nu*mu_s][4] layout, so every exchange is an in-place
-all-gather of slab views (NCCL over NVLink on GPUs; gloo in the CPU test).  This module is pure host logic: the stages
-themselves run through a backend (the CUDA library in production, see `PendingBackend`).
+The schedule lives in the C library (`fb_sharded_plan`, fuzzyblue_b200/csrc/fb_sharded.cu, where the dependency
+analysis of the shaders is written down): a list of steps per rank — stages on this rank's slab of the r axis,
+one-slice halo exchanges with the neighbouring ranks, the all-gather of scattering_density that the ray march of
+multiple_scattering needs, 1 KiB broadcasts of the irradiance rows.  Production executes it inside the library with
+NCCL over NVLink (`build_sharded` / `PendingAtmosphere.run_sharded` below are thin callers of
+`fb_atmosphere_build_sharded` / `fb_pending_run_sharded`).  `GlooExecutor` runs the SAME step list through
+`torch.distributed` point-to-point / broadcast calls on host tensors: it is what tests/test_sharded_cpu.py uses with a
+world-size-2 gloo group to prove that every cross-slab dependency is covered by a step.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+import ctypes
+from ctypes import byref, c_uint32, c_void_p
+from typing import List, Tuple
 
 from . import api
 
+SHARD_STAGE, SHARD_ALLGATHER, SHARD_HALO, SHARD_BCAST_ROWS, SHARD_JOIN = range(5)
+GATHER_RESULT, NO_PIPELINE = 1, 2
+
 S3 = (api.IMAGE_SCATTERING, api.IMAGE_DELTA_RAYLEIGH, api.IMAGE_DELTA_MIE, api.IMAGE_SCATTERING_DENSITY,
       api.IMAGE_DELTA_MULTIPLE_SCATTERING)
+
+
+class FbShardStep(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_int32), ("stage", ctypes.c_int32), ("image", ctypes.c_int32), ("order", ctypes.c_uint32),
+                ("begin", ctypes.c_uint32), ("end", ctypes.c_uint32), ("root", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+    def __repr__(self):
+        names = ("STAGE", "ALLGATHER", "HALO", "BCAST_ROWS", "JOIN")
+        return f"{names[self.op]}(stage={self.stage}, image={self.image}, order={self.order}, [{self.begin},{self.end}), root={self.root})"
 
 
 def slab_of(rank: int, world: int, r_size: int) -> Tuple[int, int]:
@@ -32,109 +41,114 @@ def slab_of(rank: int, world: int, r_size: int) -> Tuple[int, int]:
     return rank * n, (rank + 1) * n
 
 
-class PendingBackend:
-    """Production backend: stages are kernels of libfuzzyblue_b200.so on this rank's GPU, images are its device memory."""
+def plan(params: api.Parameters, rank: int, world: int, flags: int = GATHER_RESULT) -> List[FbShardStep]:
+    """The steps rank `rank` of `world` executes for `params` (pure host logic in the C library; no GPU needed)."""
+    raw = params.raw()
+    n = c_uint32()
+    api._check(api._lib().fb_sharded_plan(byref(raw), params.order, rank, world, flags, None, 0, byref(n)))
+    steps = (FbShardStep * n.value)()
+    api._check(api._lib().fb_sharded_plan(byref(raw), params.order, rank, world, flags, steps, n.value, byref(n)))
+    return list(steps)
 
-    def __init__(self, pending: api.PendingAtmosphere, stream=None):
+
+def bytes_received(params: api.Parameters, rank: int, world: int, flags: int = GATHER_RESULT) -> dict:
+    """Bytes this rank receives per precompute, by kind of exchange (for the bench's `collective` record)."""
+    R = params.scattering_r_size
+    slice_b = params.scattering_mu_size * params.scattering_nu_size * params.scattering_mu_s_size * 8
+    row_b = params.irradiance_mu_s_size * 16
+    out = {"all_gather": 0, "halo": 0, "rows": 0, "exchanges": 0}
+    for s in plan(params, rank, world, flags):
+        if s.op == SHARD_ALLGATHER:
+            out["all_gather"] += (world - 1) * (s.end - s.begin) * slice_b
+        elif s.op == SHARD_HALO:
+            out["halo"] += ((rank > 0) + (rank < world - 1)) * slice_b
+        elif s.op == SHARD_BCAST_ROWS:
+            out["rows"] += (s.end - s.begin) * row_b if s.root != rank else 0
+        if s.op in (SHARD_ALLGATHER, SHARD_HALO, SHARD_BCAST_ROWS):
+            out["exchanges"] += 1
+    out["total"] = out["all_gather"] + out["halo"] + out["rows"]
+    return out
+
+
+class NcclComm:
+    """An NCCL communicator created through the library's own thin wrappers (`fb_nccl_*`): what a caller without NCCL
+    bindings uses.  The 128-byte unique id travels from rank 0 to the others through `torch.distributed` (any backend)."""
+
+    def __init__(self, device: int, rank: int, world: int, group=None):
         import torch
-        self.pending, self.stream, self._torch = pending, stream, torch
-
-    def run_stage(self, stage: int, order: int = 0, r_begin: int = 0, r_end: int = 0):
-        self.pending.run_stage(stage, order, r_begin, r_end, self.stream)
-
-    def tensor(self, image: int):
-        """The whole image as a torch CUDA tensor aliasing the library's allocation (first dim = r for 3-D images)."""
-        torch = self._torch
-        ptr, nbytes = self.pending.image(image)
-        shape = self.pending._shape(image)
-        f16 = image in S3
-
-        class _Raw:
-            __cuda_array_interface__ = {"shape": shape, "typestr": "<f2" if f16 else "<f4", "data": (ptr, False), "version": 2}
-
-        return torch.as_tensor(_Raw(), device="cuda")
-
-
-class ShardedPrecompute:
-    """The command stream of Atmosphere::build (src/precompute.rs:1671-2048) with the 3-D stages restricted to this
-    rank's r-slab and the exchanges listed above.
-
-    The two big producers (scattering_density before K6, multiple_scattering before the next order) are launched in
-    `chunks` sub-slabs; as soon as a sub-slab has been enqueued its all-gather goes onto a communication stream, so the
-    NVLink transfer of sub-slab c overlaps the computation of sub-slab c+1 (GPU backends; the CPU test backend has no
-    streams and gathers synchronously)."""
-
-    def __init__(self, backend, r_size: int, order: int, rank: int, world: int, group=None, chunks: int = 4,
-                 min_chunk_bytes: int = 16 << 20):
-        self.b, self.order, self.rank, self.world, self.group = backend, order, rank, world, group
-        self.r0, self.r1 = slab_of(rank, world, r_size)
-        self.r_size = r_size
-        n = self.r1 - self.r0
-        self.chunks = max(c for c in range(1, max(1, min(chunks, n)) + 1) if n % c == 0)
-        if world > 1:   # splitting only pays when a sub-slab is a real transfer (>= 16 MiB); small tables go in one piece
-            t = backend.tensor(api.IMAGE_SCATTERING_DENSITY)
-            while self.chunks > 1 and (t.numel() * t.element_size() // world // self.chunks < min_chunk_bytes or n % self.chunks):
-                self.chunks -= 1
-        self.gathers = 0
-        self.bytes_received = 0          # per rank, summed over all exchanges
-        self._comm = None
-        if world > 1 and getattr(backend, "stream", None) is not None:
-            import torch
-            self._comm = torch.cuda.Stream()
-
-    def _all_gather(self, image: int, lo: int = 0, hi: int = 0):
-        """All-gather rows [lo, hi) (relative to each rank's slab; default: the whole slab) of `image`."""
-        if self.world == 1:
-            return
         import torch.distributed as dist
-        full = self.b.tensor(image)
-        n = self.r_size // self.world
-        hi = hi or n
-        views = [full[i * n + lo:i * n + hi] for i in range(self.world)]
-        if self._comm is None:
-            dist.all_gather(views, views[self.rank], group=self.group)
-        else:
-            import torch
-            ev = torch.cuda.Event()
-            ev.record(self.b.stream)                 # the sub-slab's producer kernel has been enqueued on the compute stream
-            self._comm.wait_event(ev)
-            with torch.cuda.stream(self._comm):
-                dist.all_gather(views, views[self.rank], group=self.group)
-        self.gathers += 1
-        self.bytes_received += (self.world - 1) * views[0].numel() * views[0].element_size()
+        self.rank, self.world = rank, world
+        ident = (ctypes.c_char * 128)()
+        if rank == 0:
+            api._check(api._lib().fb_nccl_unique_id(ctypes.cast(ident, c_void_p)))
+        dev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.frombuffer(bytearray(bytes(ident)), dtype=torch.uint8).clone().to(dev)
+        dist.broadcast(t, 0, group=group)
+        buf = bytes(t.cpu().numpy().tobytes())
+        h = c_void_p()
+        api._check(api._lib().fb_nccl_comm_create(device, world, rank, ctypes.c_char_p(buf), byref(h)))
+        self.handle = h.value
 
-    def _join(self):
-        """Dependent stages on the compute stream wait for every exchange issued so far."""
-        if self._comm is not None:
-            self.b.stream.wait_stream(self._comm)
+    def close(self):
+        if getattr(self, "handle", None):
+            api._lib().fb_nccl_comm_destroy(c_void_p(self.handle))
+            self.handle = None
 
-    def _produce_and_gather(self, stage: int, order: int, image: int, gather: bool = True):
-        m = (self.r1 - self.r0) // self.chunks
-        for c in range(self.chunks):
-            self.b.run_stage(stage, order, self.r0 + c * m, self.r0 + (c + 1) * m)
-            if gather:
-                self._all_gather(image, c * m, (c + 1) * m)
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
-    def run(self, gather_result: bool = True):
-        b, r0, r1 = self.b, self.r0, self.r1
-        b.run_stage(api.STAGE_TRANSMITTANCE)
-        b.run_stage(api.STAGE_DIRECT_IRRADIANCE)
-        b.run_stage(api.STAGE_SINGLE_SCATTERING, 0, r0, r1)
-        b.run_stage(api.STAGE_CLEAR_IRRADIANCE)
-        if self.order >= 2:
-            self._all_gather(api.IMAGE_DELTA_RAYLEIGH)      # order-2 density halo + indirect irradiance of order 1
-            self._all_gather(api.IMAGE_DELTA_MIE)
-            self._join()
-        for order in range(2, self.order + 1):
-            # K4 in sub-slabs, each gathered behind the next one's computation: the ray march of K6 crosses every r
-            self._produce_and_gather(api.STAGE_SCATTERING_DENSITY, order, api.IMAGE_SCATTERING_DENSITY)
-            b.run_stage(api.STAGE_INDIRECT_IRRADIANCE, order - 1)          # replicated: 2-D, reads all r (previous order)
-            self._join()
-            # K6 likewise; its output feeds the next order's density halo and indirect irradiance
-            self._produce_and_gather(api.STAGE_MULTIPLE_SCATTERING, 0, api.IMAGE_DELTA_MULTIPLE_SCATTERING,
-                                     gather=order < self.order)
-            self._join()
-        if gather_result:
-            self._all_gather(api.IMAGE_SCATTERING)
-            self._join()
+
+def build_sharded(builder: api.Builder, params: api.Parameters, comm, rank: int, world: int, flags: int = GATHER_RESULT,
+                  stream=None) -> api.PendingAtmosphere:
+    """Atmosphere::build across `world` GPUs (src/precompute.rs:1077-1081): `fb_atmosphere_build_sharded`."""
+    h = c_void_p()
+    raw = params.raw()
+    api._check(api._lib().fb_atmosphere_build_sharded(builder._h, byref(raw), params.order, c_void_p(comm.handle if comm is not None else 0),
+                                                      rank, world, flags, api._stream(stream), byref(h)))
+    return api.PendingAtmosphere(h, builder, params)
+
+
+class GlooExecutor:
+    """Runs a plan with `torch.distributed` collectives on host tensors (gloo): the CPU stand-in for the library's NCCL
+    executor.  `backend.run_stage(stage, order, begin, end)` evaluates a stage, `backend.tensor(image)` returns the whole
+    image as a tensor whose first dimension is r (3-D images) or the irradiance row (2-D images)."""
+
+    def __init__(self, backend, params: api.Parameters, rank: int, world: int, group=None):
+        self.b, self.p, self.rank, self.world, self.group = backend, params, rank, world, group
+        self.exchanges = 0
+
+    def run(self, flags: int = GATHER_RESULT):
+        import torch.distributed as dist
+        n = self.p.scattering_r_size // self.world
+        a, b = self.rank * n, (self.rank + 1) * n
+        for s in plan(self.p, self.rank, self.world, flags):
+            if s.op == SHARD_STAGE:
+                self.b.run_stage(s.stage, s.order, s.begin, s.end)
+            elif s.op == SHARD_ALLGATHER:
+                full = self.b.tensor(s.image)
+                for q in range(self.world):          # one in-place broadcast per owner, as the NCCL executor does
+                    dist.broadcast(full[q * n + s.begin:q * n + s.end], q, group=self.group)
+                self.exchanges += 1
+            elif s.op == SHARD_HALO:
+                full = self.b.tensor(s.image)
+                ops = []
+                if self.rank > 0:
+                    ops += [dist.P2POp(dist.isend, full[a].contiguous(), self.rank - 1, self.group),
+                            dist.P2POp(dist.irecv, full[a - 1], self.rank - 1, self.group)]
+                if self.rank < self.world - 1:
+                    ops += [dist.P2POp(dist.isend, full[b - 1].contiguous(), self.rank + 1, self.group),
+                            dist.P2POp(dist.irecv, full[b], self.rank + 1, self.group)]
+                for w in dist.batch_isend_irecv(ops) if ops else []:
+                    w.wait()
+                self.exchanges += 1
+            elif s.op == SHARD_BCAST_ROWS:
+                dist.broadcast(self.b.tensor(s.image)[s.begin:s.end], s.root, group=self.group)
+                self.exchanges += 1
+            elif s.op == SHARD_JOIN:
+                pass                                 # host collectives are synchronous
+            else:
+                raise ValueError(s.op)
         return self

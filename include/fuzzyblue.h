@@ -139,8 +139,15 @@ FB_API uint32_t fb_params_default_order(void);
 FB_API int fb_params_transmittance_extent(const FbParams* p, FbExtent2D* out);
 FB_API int fb_params_irradiance_extent(const FbParams* p, FbExtent2D* out);
 FB_API int fb_params_scattering_extent(const FbParams* p, FbExtent3D* out);
-/* FB_OK when the dims are usable (every size >= 2, scattering_mu_size even, products fit int32). */
+/* FB_OK when the block is usable: every size >= 2, scattering_mu_size even, products fit int32, every float finite,
+ * 0 < bottom_radius < top_radius, mu_s_min in [-1, 0], |g| < 1 (the reference checks nothing: a bad block there is
+ * undefined behaviour in the shaders). */
 FB_API int fb_params_validate(const FbParams* p);
+/* Bit s (FbStage) is set when stage s of these dims is NOT covered by the restructured kernels and runs the
+ * one-thread-per-texel transcription instead (~30x slower): scattering_density for scattering_nu_size > 128 or
+ * irradiance_mu_s_size > 512, multiple_scattering for rows of more than 8192 texels.  0 for every config of
+ * BASELINE.json.  fb_pending_slow_stages reports what a pending actually ran. */
+FB_API uint32_t fb_params_slow_stages(const FbParams* p);
 
 /* Builder::new, src/precompute.rs:61-68: one-time, device-wide setup.  `device` is a CUDA ordinal. */
 FB_API int fb_builder_create(int device, FbBuilder** out);
@@ -177,10 +184,13 @@ FB_API int fb_pending_set_readback(FbPending* p, void* host_transmittance, void*
  * (fb_atmosphere_allocate + fb_pending_run_stage) the running total since allocation. */
 FB_API int fb_pending_launch_count(const FbPending* p);
 
-/* One stage on the slab r in [r_begin, r_end) of the scattering r axis (3-D stages) or on the whole
- * table (2-D stages; slab ignored).  r_end = 0 means "to the end".  `order` is the push constant
- * the reference passes for that stage (precompute.rs:1897, :1946); ignored elsewhere. */
+/* One stage on the slab r in [r_begin, r_end) of the scattering r axis (3-D stages), on the ROWS [r_begin, r_end) of
+ * the irradiance table (indirect_irradiance) or on the whole table (the other 2-D stages; slab ignored).  r_end = 0
+ * means "to the end".  `order` is the push constant the reference passes for that stage (precompute.rs:1897, :1946);
+ * ignored elsewhere. */
 FB_API int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_begin, uint32_t r_end, void* stream);
+/* Stages (bit s = FbStage s) this pending ran on the transcription kernels although the builder asked for FAST. */
+FB_API uint32_t fb_pending_slow_stages(const FbPending* p);
 /* Device pointer + byte size of one image (linear layout above), for collectives and interop. */
 FB_API int fb_pending_image(FbPending* p, int image, void** dev_ptr, size_t* bytes);
 /* Host <-> image copies (async on `stream`; `bytes` must equal the image size). */
@@ -189,8 +199,13 @@ FB_API int fb_pending_download(FbPending* p, int image, void* host, size_t bytes
 
 /* PendingAtmosphere::atmosphere, :2203-2206 — borrowed, valid while `p` lives. */
 FB_API int fb_pending_atmosphere(FbPending* p, const FbAtmosphere** out);
-/* PendingAtmosphere::assert_ready, :2208-2211 — consumes `p`, frees the five temporaries.  The
- * caller asserts the stream has finished; pass check=1 to have it verified (FB_ERR_NOT_READY). */
+/* Blocks the calling thread until everything submitted through `p` (on any stream) has finished — the analogue of
+ * waiting for the fence of the submission that carried the command buffer (tests/smoke.rs:147-155). */
+FB_API int fb_pending_wait(FbPending* p);
+/* PendingAtmosphere::assert_ready, :2208-2211 — consumes `p`, frees the five temporaries.  The caller asserts the
+ * stream has finished.  check=1 verifies it with an event query (no synchronisation): FB_ERR_NOT_READY if work is
+ * still in flight, and `p` stays valid.  check=0 trusts the caller as the reference does; the temporaries are then
+ * recycled stream-ordered, so a too-early call cannot corrupt a later precompute. */
 FB_API int fb_pending_assert_ready(FbPending* p, int check, FbAtmosphere** out);
 /* Drop for PendingAtmosphere, :2122-2140 (also drops the atmosphere if it was never taken). */
 FB_API void fb_pending_destroy(FbPending* p);
@@ -247,8 +262,9 @@ FB_API int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, v
 /* Renderer::new, src/render.rs:34-40 (render pass / subpass / frame count have no CUDA meaning).
  * A renderer keeps device scratch of its own: the draw blocks of a sweep and, for draws of at least one pixel per
  * scattering texel, an fp32 (value, delta) expansion of the scattering table it last drew from (32 bytes per texel,
- * up to 256 MiB; bit-identical look-ups at half the instructions).  The expansion is re-derived, after a device-wide
- * synchronisation, when a draw names other table contents, so alternate between atmospheres with one renderer each.
+ * up to 256 MiB; bit-identical look-ups at half the instructions).  The expansion is re-derived when a draw names other
+ * table contents (the rebuild waits on the device for earlier draws, no host synchronisation), so alternate between
+ * atmospheres with one renderer each.
  * As with the reference's Renderer (descriptor sets per frame, render.rs:34-40), draws through one renderer are
  * externally synchronised by the caller. */
 FB_API int fb_renderer_create(FbBuilder* b, FbRenderer** out);
@@ -286,6 +302,53 @@ FB_API int fb_sun_and_sky_irradiance(const FbAtmosphere* a, const float* point, 
  * each, round-robin over an internal pool of streams that all fork from / join into `stream`. */
 FB_API int fb_atmosphere_build_batch(FbBuilder* b, const FbParams* params, uint32_t n, uint32_t order, void* stream,
                                      FbPending** out /* [n] */);
+
+/* ---- One atmosphere built by several GPUs (BASELINE.json configs[2]): the scattering table slabbed along r ---------
+ * The multi-device replacement for Atmosphere::build (src/precompute.rs:1077-1081).  Rank `rank` of `world` owns the
+ * altitude levels [rank * R / world, (rank + 1) * R / world) of every 3-D image (R = scattering_r_size must divide by
+ * `world`); a slab is one contiguous byte range of the linear layout.  Per scattering order the ranks exchange
+ *   - an all-gather of scattering_density before multiple_scattering (its ray march crosses every r:
+ *     multiple_scattering.comp:35-44), pipelined in sub-slabs behind the density kernels,
+ *   - a one-slice halo of delta_multiple_scattering (delta_rayleigh / delta_mie once) with each neighbour: a density
+ *     texel reads the previous order's table at its own r +- one slice (scattering_density.comp:72-75, scattering.h:17-22),
+ *   - the irradiance rows, each computed by the rank whose slab brackets its altitude, as 1 KiB broadcasts.
+ * The schedule is data: fb_sharded_plan writes the steps rank `rank` executes (no device needed); fb_pending_run_sharded
+ * executes them with NCCL on `stream` + an internal communication stream.  Results are bit-identical to the
+ * single-GPU build (tests/test_sharded_gpu.py). */
+typedef enum FbShardOp {
+    FB_SHARD_STAGE = 0,      /* fb_pending_run_stage(stage, order, begin, end)                                             */
+    FB_SHARD_ALLGATHER = 1,  /* 3-D `image`: rows [begin, end) RELATIVE to each rank's slab, every rank to every rank     */
+    FB_SHARD_HALO = 2,       /* 3-D `image`: my first slice -> rank - 1, my last slice -> rank + 1; theirs into my halo    */
+    FB_SHARD_BCAST_ROWS = 3, /* 2-D `image`: rows [begin, end) from rank `root` to everyone                               */
+    FB_SHARD_JOIN = 4        /* later stages wait for every exchange issued so far                                        */
+} FbShardOp;
+typedef struct FbShardStep {
+    int32_t op;     /* FbShardOp */
+    int32_t stage;  /* FbStage (FB_SHARD_STAGE) */
+    int32_t image;  /* FbImage (exchanges) */
+    uint32_t order; /* push constant of the stage */
+    uint32_t begin, end;
+    int32_t root;
+    int32_t _pad;
+} FbShardStep;
+#define FB_SHARD_GATHER_RESULT 1u /* finish with an all-gather of `scattering`: every rank ends with the whole table */
+#define FB_SHARD_NO_PIPELINE 2u   /* exchange whole slabs (one ncclAllGather) instead of sub-slabs behind the kernels */
+/* steps = NULL: only *count is written.  Transmittance and irradiance always end complete on every rank. */
+FB_API int fb_sharded_plan(const FbParams* p, uint32_t order, int rank, int world, uint32_t flags, FbShardStep* steps,
+                           uint32_t capacity, uint32_t* count);
+/* `nccl_comm` is an ncclComm_t of `world` ranks in which this process is `rank` (NULL allowed when world == 1).
+ * NCCL is loaded at run time (libnccl.so.2, or $FUZZYBLUE_B200_NCCL_LIB): no link-time dependency. */
+FB_API int fb_atmosphere_build_sharded(FbBuilder* b, const FbParams* p, uint32_t order, void* nccl_comm, int rank, int world,
+                                       uint32_t flags, void* stream, FbPending** out);
+/* The same schedule again on the images `p` already owns (what a benchmark loop times). */
+FB_API int fb_pending_run_sharded(FbPending* p, void* nccl_comm, int rank, int world, uint32_t flags, void* stream);
+/* For callers without NCCL bindings of their own (ctypes, C): thin wrappers over ncclGetUniqueId / ncclCommInitRank /
+ * ncclCommDestroy.  Rank 0 makes the id and ships its 128 bytes to the other ranks by any means. */
+#define FB_NCCL_UNIQUE_ID_BYTES 128
+FB_API int fb_nccl_version(int* version);
+FB_API int fb_nccl_unique_id(void* id128);
+FB_API int fb_nccl_comm_create(int device, int world, int rank, const void* id128, void** nccl_comm_out);
+FB_API int fb_nccl_comm_destroy(void* nccl_comm);
 
 #ifdef __cplusplus
 }

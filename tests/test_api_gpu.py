@@ -88,8 +88,7 @@ def test_non_multiple_of_workgroup_dims_are_fully_written():
         assert np.all(np.isfinite(S.astype(np.float32))) and (S.astype(np.float32)[..., :3] > 0).mean() > 0.5
         assert np.all(np.isfinite(E)) and E.max() > 0
     from oracle import oracle as O
-    # second set: nu_size = 3 is not a power of two, so the product family's density stage falls back to the
-    # one-thread-per-texel kernel while every other stage stays on the fast path
+    # second set: nu_size = 3 is not a power of two (a mu_s tile of the density kernel is then found by division)
     for d in (dims, dict(dims, scattering_nu_size=3, scattering_mu_s_size=5)):
         ref = O.precompute(O.Params(order=3, **d), O.F32)
         Tf, Sf, Ef = fb.precompute_host(fb.Builder(0), fb.Parameters(order=3, **d))
@@ -131,3 +130,98 @@ def test_exported_allocation_carries_the_tables():
     with pytest.raises(fb.FuzzyblueError):
         atm.export_fd()
     atm.close()
+
+
+def test_assert_ready_reports_not_ready_and_waits():
+    """fb_pending_assert_ready(check = 1) queries the completion events of the precompute: FB_ERR_NOT_READY while kernels
+    are in flight (the pending stays usable), success after fb_pending_wait -- no device-wide synchronisation."""
+    import torch
+    b = fb.Builder(0)
+    s = torch.cuda.Stream()
+    pend = fb.Atmosphere.build(b, s, fb.Parameters())
+    for _ in range(20):
+        pend.resubmit(s)                       # ~60 ms of queued device work
+    with pytest.raises(fb.FuzzyblueError) as ei:
+        pend.assert_ready(check=True, wait=False)
+    assert ei.value.status == 5                # FB_ERR_NOT_READY
+    assert pend.launch_count() > 0             # still a valid object
+    pend.wait()
+    atm = pend.assert_ready(check=True, wait=False)
+    assert np.all(np.isfinite(atm.read_irradiance()))
+
+
+def test_block_reuse_is_stream_ordered():
+    """a released block may still be written by kernels in flight.  Drop a pending early
+    (check = 0, work queued on its stream), immediately build another atmosphere of the same dims on ANOTHER stream -- it
+    receives the cached blocks -- and its tables must equal an undisturbed build bit for bit."""
+    import torch
+    b = fb.Builder(0)
+    p = fb.Parameters(**SMOKE_DIMS)
+    want = fb.precompute_host(b, p)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(4):
+        victim = fb.Atmosphere.build(b, s1, fb.Parameters(order=6, **SMOKE_DIMS))
+        for _ in range(10):
+            victim.resubmit(s1)
+        a0 = victim.assert_ready(check=False)  # temporaries go back to the cache with kernels still queued
+        a0.close()                             # ... and so does the kept block
+        pend = fb.Atmosphere.build(b, s2, p)   # same dims: served from the cache
+        pend.wait()
+        atm = pend.assert_ready()
+        assert np.array_equal(atm.read_scattering().view(np.uint16), want[1].view(np.uint16))
+        assert np.array_equal(atm.read_irradiance(), want[2])
+        atm.close()
+
+
+def test_pending_outlives_its_builder():
+    """FbPending copied what it needs from the Builder; destroying the builder first is legal."""
+    import torch
+    b = fb.Builder(0)
+    pend = fb.Atmosphere.build(b, None, fb.Parameters(**SMOKE_DIMS))
+    api._lib().fb_builder_destroy(b._h)
+    b._h = None
+    pend.resubmit(None)
+    pend.run_stage(api.STAGE_TRANSMITTANCE)
+    torch.cuda.synchronize()
+    assert np.all(np.isfinite(pend.download(api.IMAGE_SCATTERING).astype(np.float32)))
+    pend.close()
+
+
+@pytest.mark.parametrize("nu,mu_s", [(3, 5), (6, 12), (12, 8), (5, 32)])
+def test_non_power_of_two_nu_runs_the_fast_kernels(nu, mu_s):
+    """nu_size need not be a power of two for the restructured density kernel (a mu_s tile is T / nu
+    columns, found by division); the result matches the oracle and NO stage falls back to the transcription."""
+    from oracle import oracle as O
+    d = dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=mu_s, scattering_nu_size=nu)
+    ref = O.precompute(O.Params(order=3, **d), O.F32, keep_history=True)
+    b = fb.Builder(0)
+    pend = fb.Atmosphere.allocate(b, fb.Parameters(order=3, **d))
+    assert api._lib().fb_params_slow_stages(ctypes.byref(fb.Parameters(order=3, **d).raw())) == 0
+    for order in (2, 3):
+        prev = ref.history["single"] if order == 2 else ref.history[order - 1]
+        pend.upload(api.IMAGE_TRANSMITTANCE, ref.transmittance)
+        pend.upload(api.IMAGE_DELTA_RAYLEIGH, ref.delta_rayleigh)
+        pend.upload(api.IMAGE_DELTA_MIE, ref.delta_mie)
+        pend.upload(api.IMAGE_DELTA_IRRADIANCE, prev["delta_irradiance"])
+        if order > 2:
+            pend.upload(api.IMAGE_DELTA_MULTIPLE_SCATTERING, prev["delta_multiple_scattering"])
+        n0 = pend.launch_count()
+        pend.run_stage(api.STAGE_SCATTERING_DENSITY, order=order)
+        assert pend.launch_count() - n0 == 2               # k_density_prep + k_density_main, not the 1-launch transcription
+        got = pend.download(api.IMAGE_SCATTERING_DENSITY).astype(np.float64)
+        want = ref.history[order]["scattering_density"]
+        e = np.abs(got - want) / np.maximum(np.abs(want), 2.0 ** -14)
+        assert e.max() <= 1e-3, (nu, mu_s, order, e.max())
+    assert pend.slow_stages() == 0
+
+
+def test_slow_stage_cliffs_are_reported():
+    """Dims the restructured kernels do not cover run the transcription -- and say so (fb_pending_slow_stages)."""
+    d = dict(scattering_r_size=2, scattering_mu_size=4, scattering_mu_s_size=2, scattering_nu_size=2, irradiance_mu_s_size=520,
+             irradiance_r_size=4)
+    p = fb.Parameters(order=2, **d)
+    assert api._lib().fb_params_slow_stages(ctypes.byref(p.raw())) == 1 << api.STAGE_SCATTERING_DENSITY
+    pend = fb.Atmosphere.build(fb.Builder(0), None, p)
+    pend.wait()
+    assert pend.slow_stages() == 1 << api.STAGE_SCATTERING_DENSITY
+    assert fb.Atmosphere.build(fb.Builder(0), None, fb.Parameters(**SMOKE_DIMS)).slow_stages() == 0

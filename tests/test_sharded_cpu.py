@@ -1,8 +1,10 @@
-"""world_size-2 gloo test of the r-slab sharding host logic (fuzzyblue_b200/sharded.py) on CPU.
+"""world_size-2 gloo test of the r-slab sharded schedule on CPU.
 
-The stages run through an oracle-backed stand-in for the CUDA backend (the oracle is test infrastructure; the
-product backend is PendingBackend).  The sharded schedule + all-gathers must reproduce the single-process tables
-EXACTLY, which proves every cross-slab dependency is covered by an exchange."""
+The schedule is `fb_sharded_plan` of the C library (fuzzyblue_b200/csrc/fb_sharded.cu: pure host logic, runs without a
+GPU); `sharded.GlooExecutor` executes its steps with gloo collectives, the stages themselves through an oracle-backed
+stand-in for the CUDA kernels (the oracle is test infrastructure; production runs the same step list inside the library
+with NCCL).  Every slab a rank never computes starts as NaN, so a dependency the plan does not cover with an exchange
+poisons the result: the sharded tables must equal the single-process tables EXACTLY."""
 import os
 import sys
 
@@ -15,6 +17,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+import fuzzyblue_b200 as fb               # noqa: E402
 from fuzzyblue_b200 import api, sharded   # noqa: E402
 from oracle import oracle as O            # noqa: E402
 
@@ -30,6 +33,7 @@ class OracleBackend:
         shapes = {api.IMAGE_TRANSMITTANCE: p.t_shape, api.IMAGE_IRRADIANCE: p.e_shape, api.IMAGE_DELTA_IRRADIANCE: p.e_shape}
         # slabs this rank never computes stay NaN until an all-gather fills them: a missing exchange poisons the result
         self.img = {i: torch.full(shapes.get(i, p.s_shape), float("nan"), dtype=torch.float64) for i in range(8)}
+        self.rows_computed = 0
 
     def tensor(self, image):
         return self.img[image]
@@ -65,10 +69,15 @@ class OracleBackend:
                                        dms, g(api.IMAGE_DELTA_IRRADIANCE), idx)
             g(api.IMAGE_SCATTERING_DENSITY)[r0:r1] = out.reshape(shp)
         elif stage == api.STAGE_INDIRECT_IRRADIANCE:
+            # rows [r_begin, r_end) of the irradiance table only; the oracle evaluates every row (rows of other ranks read
+            # NaN slabs and come out NaN) and the rows this rank owns are kept
+            e0, e1 = r_begin, (r_end or p.irradiance_r_size)
             dms = g(api.IMAGE_DELTA_MULTIPLE_SCATTERING) if order > 1 else np.zeros(p.s_shape)
-            dE, E = O.indirect_irradiance(p, m, order, g(api.IMAGE_DELTA_RAYLEIGH), g(api.IMAGE_DELTA_MIE), dms, g(api.IMAGE_IRRADIANCE))
-            g(api.IMAGE_DELTA_IRRADIANCE)[:] = dE
-            g(api.IMAGE_IRRADIANCE)[:] = E
+            with np.errstate(all="ignore"):
+                dE, E = O.indirect_irradiance(p, m, order, g(api.IMAGE_DELTA_RAYLEIGH), g(api.IMAGE_DELTA_MIE), dms, g(api.IMAGE_IRRADIANCE))
+            g(api.IMAGE_DELTA_IRRADIANCE)[e0:e1] = dE[e0:e1]
+            g(api.IMAGE_IRRADIANCE)[e0:e1] = E[e0:e1]
+            self.rows_computed += e1 - e0
         elif stage == api.STAGE_MULTIPLE_SCATTERING:
             S_in = np.nan_to_num(g(api.IMAGE_SCATTERING), nan=0.0)
             dMS, S = O.multiple_scattering(p, m, g(api.IMAGE_TRANSMITTANCE), g(api.IMAGE_SCATTERING_DENSITY), S_in, idx)
@@ -78,14 +87,15 @@ class OracleBackend:
             raise ValueError(stage)
 
 
-def _worker(rank, world, port, order, out_dir, min_chunk_bytes):
+def _worker(rank, world, port, order, out_dir, flags):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     p = O.Params(order=order, **DIMS)
     be = OracleBackend(p)
-    sp = sharded.ShardedPrecompute(be, p.scattering_r_size, order, rank, world, min_chunk_bytes=min_chunk_bytes).run()
+    ex = sharded.GlooExecutor(be, fb.Parameters(order=order, **DIMS), rank, world).run(flags)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), S=be._np(api.IMAGE_SCATTERING), E=be._np(api.IMAGE_IRRADIANCE),
-             T=be._np(api.IMAGE_TRANSMITTANCE), dMS=be._np(api.IMAGE_DELTA_MULTIPLE_SCATTERING), gathers=sp.gathers)
+             T=be._np(api.IMAGE_TRANSMITTANCE), dMS=be._np(api.IMAGE_DELTA_MULTIPLE_SCATTERING), exchanges=ex.exchanges,
+             rows=be.rows_computed)
     dist.destroy_process_group()
 
 
@@ -96,24 +106,78 @@ def test_slab_partition():
         sharded.slab_of(0, 3, 32)
 
 
-@pytest.mark.parametrize("order,min_chunk_bytes", [(3, 16 << 20), (3, 0)])
-def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order, min_chunk_bytes):
-    """min_chunk_bytes = 0 forces the sub-slab pipeline (2 chunks per 2-row slab) that large tables use."""
-    world, port = 2, 29500 + (os.getpid() % 2000) + (1 if min_chunk_bytes else 0)
-    mp.spawn(_worker, args=(world, port, order, str(tmp_path), min_chunk_bytes), nprocs=world, join=True)
-    chunks = 1 if min_chunk_bytes else 2
+def _steps(p, rank, world, flags=sharded.GATHER_RESULT):
+    return [(s.op, s.stage, s.image, s.order, s.begin, s.end, s.root) for s in sharded.plan(p, rank, world, flags)]
+
+
+def test_plan_single_rank_is_the_reference_schedule():
+    """world = 1: no exchanges, and the stages are the recorded command stream of src/precompute.rs:1671-2048."""
+    p = fb.Parameters(order=4)
+    st = _steps(p, 0, 1)
+    assert all(op == sharded.SHARD_STAGE for op, *_ in st)
+    want = [api.STAGE_TRANSMITTANCE, api.STAGE_DIRECT_IRRADIANCE, api.STAGE_SINGLE_SCATTERING, api.STAGE_CLEAR_IRRADIANCE]
+    for _ in (2, 3, 4):
+        want += [api.STAGE_SCATTERING_DENSITY, api.STAGE_INDIRECT_IRRADIANCE, api.STAGE_MULTIPLE_SCATTERING]
+    assert [s[1] for s in st] == want
+    assert [s[3] for s in st if s[1] == api.STAGE_SCATTERING_DENSITY] == [2, 3, 4]         # push constant `order`
+    assert [s[3] for s in st if s[1] == api.STAGE_INDIRECT_IRRADIANCE] == [1, 2, 3]        # push constant `order - 1`
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_plan_properties(world):
+    """Default and high-resolution dims: the slabs tile the r axis, the irradiance rows are partitioned, every rank issues
+    the same exchanges in the same order (a collective the ranks disagree on would deadlock), and the bytes a rank
+    receives are the one mandatory all-gather per order plus halos."""
+    hires = dict(transmittance_mu_size=1024, transmittance_r_size=256, scattering_r_size=128, scattering_mu_size=512,
+                 scattering_mu_s_size=128, scattering_nu_size=32)
+    for p in (fb.Parameters(order=4), fb.Parameters(order=8, **hires)):
+        plans = [_steps(p, r, world) for r in range(world)]
+        R = p.scattering_r_size
+        slabs = sorted((s[4], s[5]) for pl in plans for s in pl if s[0] == sharded.SHARD_STAGE and s[1] == api.STAGE_SINGLE_SCATTERING)
+        assert slabs == [(r * R // world, (r + 1) * R // world) for r in range(world)]
+        rows = sorted((s[4], s[5]) for pl in plans for s in pl
+                      if s[0] == sharded.SHARD_STAGE and s[1] == api.STAGE_INDIRECT_IRRADIANCE and s[3] == 1)
+        assert rows[0][0] == 0 and rows[-1][1] == p.irradiance_r_size
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(len(rows) - 1))             # a partition of the rows
+        exch = [[s for s in pl if s[0] != sharded.SHARD_STAGE] for pl in plans]
+        assert all(e == exch[0] for e in exch)
+        got = sharded.bytes_received(p, 1, world)
+        table = R * p.scattering_mu_size * p.scattering_nu_size * p.scattering_mu_s_size * 8
+        assert got["all_gather"] == (world - 1) * table // world * (p.order - 1 + 1)          # density per order + the result
+        assert got["halo"] <= 2 * (table // R) * (2 + p.order - 2)
+    # 2 GiB tables are exchanged in sub-slabs behind the density kernels, 8 MiB tables in one piece
+    n_gather = lambda p, flags: sum(1 for s in _steps(p, 0, 8, flags) if s[0] == sharded.SHARD_ALLGATHER and s[2] == api.IMAGE_SCATTERING_DENSITY)
+    assert n_gather(fb.Parameters(order=8, **hires), 0) == 7 * 4 and n_gather(fb.Parameters(order=8, **hires), sharded.NO_PIPELINE) == 7
+    assert n_gather(fb.Parameters(order=4), 0) == 3
+
+
+def test_plan_rejects_uneven_slabs():
+    with pytest.raises(fb.FuzzyblueError):
+        sharded.plan(fb.Parameters(), 0, 3)
+    with pytest.raises(fb.FuzzyblueError):
+        sharded.plan(fb.Parameters(), 2, 2)
+
+
+@pytest.mark.parametrize("order", [3, 4])
+def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order):
+    world, port = 2, 29500 + (os.getpid() % 2000) + order
+    mp.spawn(_worker, args=(world, port, order, str(tmp_path), sharded.GATHER_RESULT), nprocs=world, join=True)
     ref = O.precompute(O.Params(order=order, **DIMS), O.F32)
+    rows = 0
     for rank in range(world):
         got = np.load(tmp_path / f"rank{rank}.npz")
         assert np.array_equal(got["T"], ref.transmittance)
-        assert np.array_equal(got["E"], ref.irradiance)
+        assert np.array_equal(got["E"], ref.irradiance)           # rows computed by their owners, broadcast to everyone
         assert np.array_equal(got["S"], ref.scattering)           # every rank holds the full, identical final table
-        # 2 single-scattering gathers + per order: density (+ delta_multiple except after the last) + the final table
-        # (tables this small are exchanged in one piece)
-        assert int(got["gathers"]) == 2 + chunks * ((order - 1) + (order - 2)) + 1
-    # each rank's own slab of the last delta_multiple_scattering is current; the peer's slab is still the previous
-    # order's (the last order's temporaries are not exchanged: nothing reads them)
+        rows += int(got["rows"])
+        # 2 single-scattering halos; per order: the density all-gather, (before the next order) the two ground rows of
+        # delta_irradiance and the halo of delta_multiple_scattering; finally the irradiance rows of both ranks + the table
+        assert int(got["exchanges"]) == 2 + (order - 1) + (order - 2) * 3 + world + 1
+    assert rows == (order - 1) * DIMS["irradiance_r_size"]          # every irradiance row evaluated exactly once per order
+    # each rank's own slab of the last delta_multiple_scattering is current; of the peer's slab only the halo slice was
+    # ever received, and that one order earlier (the last order's temporaries are not exchanged: nothing reads them)
     r0 = np.load(tmp_path / "rank0.npz")["dMS"]
     prev = O.precompute(O.Params(order=order - 1, **DIMS), O.F32)
     assert np.array_equal(r0[:2], ref.delta_multiple_scattering[:2])
-    assert np.array_equal(r0[2:], prev.delta_multiple_scattering[2:])
+    assert np.array_equal(r0[2], prev.delta_multiple_scattering[2])
+    assert np.all(np.isnan(r0[3]))
