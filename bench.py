@@ -139,6 +139,26 @@ def ncu_dram_traffic():
     return (None, "no ncu capture found")
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  NCCL (its version banner, whatever NCCL_DEBUG asks for) and other native
+    libraries write to file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the line is
+    written to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -174,7 +194,7 @@ def run_reference(args, rank: int):
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
             "reference_unavailable": "Rust+GLSL/Vulkan reference cannot be built or run in this image (no cargo, shaderc, "
                                      "Vulkan loader or ICD); lavapipe and B200-Vulkan baselines are unavailable"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -337,7 +357,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                             "pinned host memory (fb_pending_set_readback), host wall clock from submit to stream sync"},
             "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "render": render, "hires": hires}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -429,7 +449,7 @@ def run_hires(args, rank: int, local_rank: int, world: int):
     args.hires_steps = args.steps
     line = hires_leg(args, fb.Builder(local_rank), rank, local_rank, world, dev)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -495,7 +515,7 @@ def run_batch(args, rank: int, local_rank: int, world: int):
                 "config": {"workload": f"{total} distinct atmospheres (BASELINE.json configs[3]), {len(mine)} per GPU, 32 in flight",
                            "timing": "wall clock around the whole pass incl. allocation, max over ranks", "kernels": "FAST"},
                 "atmospheres_per_second": total / sec, "results_finite": finite, "gpu_launches": 16 * len(mine) * args.steps}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -647,8 +667,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    claim_stdout()
     if world > 1:
-        # stdout carries exactly one JSON line: whatever NCCL_DEBUG makes NCCL print (its version banner) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args, rank)
