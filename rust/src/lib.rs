@@ -1,12 +1,38 @@
 //! Drop-in shim: the six public names of Ralith/fuzzyblue (`src/lib.rs:8-12`) implemented over the C ABI of
-//! `include/fuzzyblue.h`.  A CUDA stream (`*mut c_void`, null = default stream) stands where the reference takes a
-//! `vk::CommandBuffer`; device pointers stand where it returns `vk::Image`s.  The four Vulkan-only fields of
-//! `Parameters` are kept (as plain integers) so struct-update call sites such as `tests/smoke.rs:136-142` compile.
+//! `include/fuzzyblue.h`, with the reference's signatures (names, arity, argument order):
 //!
-//! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Rust toolchain); the ABI it binds is exercised by the Python and C++
-//! mirrors in the test-suite.
+//! | reference (ash 0.31)                                                                  | here                                   |
+//! |---|---|
+//! | `Builder::new(&Instance, Arc<Device>, PipelineCache, PhysicalDevice, u32, Option<u32>)` | same six arguments; the Vulkan handles are generic and ignored, the CUDA ordinal comes from `$FUZZYBLUE_B200_DEVICE` (default 0) or `Builder::with_cuda_device` |
+//! | `Atmosphere::build(Arc<Builder>, vk::CommandBuffer, &Parameters)`                     | same; `vk::CommandBuffer` is [`vk::CommandBuffer`] = a CUDA stream handle (null = default stream) |
+//! | `PendingAtmosphere::{acquire_ownership, atmosphere, assert_ready}`                     | same |
+//! | `Atmosphere::{transmittance, scattering, irradiance}{,_extent}()`                      | device pointers to the linear tables instead of `vk::Image` (`*_view()` returns the same pointer) |
+//! | `Renderer::new(&Builder, PipelineCache, RenderPass, subpass, frames)`                  | same five arguments |
+//! | `Renderer::set_depth_buffer(&mut self, frame, &vk::DescriptorImageInfo)`               | same; [`vk::DescriptorImageInfo`] carries the device pointer of the `[h][w]` f32 depth buffer |
+//! | `Renderer::draw(&self, cmd, &Atmosphere, frame, &DrawParameters)`                      | same four arguments; the two fragment outputs go to the targets set with `Renderer::set_targets` (the render pass attachments of the reference) |
+//!
+//! The four Vulkan-only fields of `Parameters` are kept (as plain integers) so struct-update call sites such as
+//! `tests/smoke.rs:136-142` compile.
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Rust toolchain).  `tests/test_rust_ffi.py` parses the `extern "C"` block
+//! and the `#[repr(C)]` structs below and checks them against `include/fuzzyblue.h` (names, arity, argument types,
+//! struct sizes); the ABI itself is exercised by the Python, C and C++ callers in the test-suite.
 use std::os::raw::{c_char, c_int, c_void};
 use std::sync::Arc;
+
+/// Stand-ins for the `ash::vk` types the reference's signatures name.
+pub mod vk {
+    use std::os::raw::c_void;
+    /// Where the reference records into a command buffer, work is enqueued on this CUDA stream (`cudaStream_t`).
+    pub type CommandBuffer = *mut c_void;
+    #[derive(Debug, Default, Copy, Clone)] pub struct PipelineCache;
+    #[derive(Debug, Default, Copy, Clone)] pub struct PhysicalDevice;
+    #[derive(Debug, Default, Copy, Clone)] pub struct RenderPass;
+    /// `set_depth_buffer` takes the depth attachment: here the device pointer of a `[height][width]` f32 buffer.
+    #[derive(Debug, Copy, Clone)] pub struct DescriptorImageInfo { pub depth: *const f32, pub width: u32, pub height: u32 }
+    #[derive(Debug, Default, Copy, Clone, PartialEq, Eq)] pub struct Extent2D { pub width: u32, pub height: u32 }
+    #[derive(Debug, Default, Copy, Clone, PartialEq, Eq)] pub struct Extent3D { pub width: u32, pub height: u32, pub depth: u32 }
+}
 
 #[allow(non_camel_case_types)]
 pub mod ffi {
@@ -38,28 +64,74 @@ pub mod ffi {
     pub struct FbExportLayout { pub allocation_bytes: usize, pub scattering_offset: usize, pub scattering_bytes: usize,
                                 pub transmittance_offset: usize, pub transmittance_bytes: usize,
                                 pub irradiance_offset: usize, pub irradiance_bytes: usize }
-    pub enum FbBuilder {} pub enum FbPending {} pub enum FbAtmosphere {} pub enum FbRenderer {}
+    #[repr(C)] #[derive(Copy, Clone, Default)]
+    pub struct FbShardStep { pub op: i32, pub stage: i32, pub image: i32, pub order: u32, pub begin: u32, pub end: u32, pub root: i32, pub _pad: i32 }
+    pub enum FbBuilder {} pub enum FbPending {} pub enum FbAtmosphere {} pub enum FbRenderer {} pub enum FbExternalSemaphore {}
+    // every FB_API function of include/fuzzyblue.h (generated by tools/gen_rust_ffi.py; checked by tests/test_rust_ffi.py)
     extern "C" {
+        pub fn fb_status_string(status: c_int) -> *const c_char;
         pub fn fb_last_error() -> *const c_char;
+        pub fn fb_version() -> *const c_char;
+        pub fn fb_params_default(out: *mut FbParams) -> c_int;
+        pub fn fb_params_default_order() -> u32;
+        pub fn fb_params_transmittance_extent(p: *const FbParams, out: *mut FbExtent2D) -> c_int;
+        pub fn fb_params_irradiance_extent(p: *const FbParams, out: *mut FbExtent2D) -> c_int;
+        pub fn fb_params_scattering_extent(p: *const FbParams, out: *mut FbExtent3D) -> c_int;
+        pub fn fb_params_validate(p: *const FbParams) -> c_int;
+        pub fn fb_params_slow_stages(p: *const FbParams) -> u32;
         pub fn fb_builder_create(device: c_int, out: *mut *mut FbBuilder) -> c_int;
         pub fn fb_builder_destroy(b: *mut FbBuilder);
+        pub fn fb_builder_set_kernels(b: *mut FbBuilder, kernels: c_int) -> c_int;
+        pub fn fb_builder_trim(b: *mut FbBuilder) -> c_int;
+        pub fn fb_builder_device(b: *const FbBuilder) -> c_int;
+        pub fn fb_builder_sm_count(b: *const FbBuilder) -> c_int;
+        pub fn fb_builder_measure_peaks(b: *mut FbBuilder, fp32_fma_tflops: *mut f64, sfu_gops: *mut f64) -> c_int;
         pub fn fb_atmosphere_build(b: *mut FbBuilder, p: *const FbParams, order: u32, stream: *mut c_void, out: *mut *mut FbPending) -> c_int;
+        pub fn fb_atmosphere_allocate(b: *mut FbBuilder, p: *const FbParams, order: u32, out: *mut *mut FbPending) -> c_int;
         pub fn fb_pending_resubmit(p: *mut FbPending, stream: *mut c_void) -> c_int;
-        pub fn fb_pending_set_readback(p: *mut FbPending, t: *mut c_void, s: *mut c_void, e: *mut c_void) -> c_int;
+        pub fn fb_pending_set_readback(p: *mut FbPending, host_transmittance: *mut c_void, host_scattering: *mut c_void, host_irradiance: *mut c_void) -> c_int;
+        pub fn fb_pending_launch_count(p: *const FbPending) -> c_int;
+        pub fn fb_pending_run_stage(p: *mut FbPending, stage: c_int, order: u32, r_begin: u32, r_end: u32, stream: *mut c_void) -> c_int;
+        pub fn fb_pending_slow_stages(p: *const FbPending) -> u32;
+        pub fn fb_pending_image(p: *mut FbPending, image: c_int, dev_ptr: *mut *mut c_void, bytes: *mut usize) -> c_int;
+        pub fn fb_pending_upload(p: *mut FbPending, image: c_int, host: *const c_void, bytes: usize, stream: *mut c_void) -> c_int;
+        pub fn fb_pending_download(p: *mut FbPending, image: c_int, host: *mut c_void, bytes: usize, stream: *mut c_void) -> c_int;
         pub fn fb_pending_atmosphere(p: *mut FbPending, out: *mut *const FbAtmosphere) -> c_int;
+        pub fn fb_pending_wait(p: *mut FbPending) -> c_int;
         pub fn fb_pending_assert_ready(p: *mut FbPending, check: c_int, out: *mut *mut FbAtmosphere) -> c_int;
         pub fn fb_pending_destroy(p: *mut FbPending);
-        pub fn fb_atmosphere_transmittance(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent2D) -> c_int;
-        pub fn fb_atmosphere_scattering(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent3D) -> c_int;
-        pub fn fb_atmosphere_irradiance(a: *const FbAtmosphere, ptr: *mut *const c_void, e: *mut FbExtent2D) -> c_int;
+        pub fn fb_atmosphere_transmittance(a: *const FbAtmosphere, dev_ptr: *mut *const c_void, extent: *mut FbExtent2D) -> c_int;
+        pub fn fb_atmosphere_scattering(a: *const FbAtmosphere, dev_ptr: *mut *const c_void, extent: *mut FbExtent3D) -> c_int;
+        pub fn fb_atmosphere_irradiance(a: *const FbAtmosphere, dev_ptr: *mut *const c_void, extent: *mut FbExtent2D) -> c_int;
+        pub fn fb_atmosphere_params(a: *const FbAtmosphere, out: *mut FbParams) -> c_int;
+        pub fn fb_atmosphere_read_transmittance(a: *const FbAtmosphere, host: *mut c_void, bytes: usize, stream: *mut c_void) -> c_int;
+        pub fn fb_atmosphere_read_scattering(a: *const FbAtmosphere, host: *mut c_void, bytes: usize, stream: *mut c_void) -> c_int;
+        pub fn fb_atmosphere_read_irradiance(a: *const FbAtmosphere, host: *mut c_void, bytes: usize, stream: *mut c_void) -> c_int;
         pub fn fb_atmosphere_destroy(a: *mut FbAtmosphere);
-        // Vulkan interop: the kept block as OPAQUE_FD-importable device memory
         pub fn fb_builder_set_exportable(b: *mut FbBuilder, on: c_int) -> c_int;
         pub fn fb_atmosphere_export_fd(a: *const FbAtmosphere, fd: *mut c_int, layout: *mut FbExportLayout) -> c_int;
+        pub fn fb_external_memory_read_fd(device: c_int, fd: c_int, allocation_bytes: usize, offset: usize, host: *mut c_void, bytes: usize) -> c_int;
+        pub fn fb_external_semaphore_import_fd(device: c_int, fd: c_int, is_timeline: c_int, out: *mut *mut FbExternalSemaphore) -> c_int;
+        pub fn fb_external_semaphore_signal(s: *mut FbExternalSemaphore, value: u64, stream: *mut c_void) -> c_int;
+        pub fn fb_external_semaphore_wait(s: *mut FbExternalSemaphore, value: u64, stream: *mut c_void) -> c_int;
+        pub fn fb_external_semaphore_destroy(s: *mut FbExternalSemaphore);
+        pub fn fb_precompute_host(b: *mut FbBuilder, p: *const FbParams, order: u32, transmittance_f32: *mut c_void, scattering_f16: *mut c_void, irradiance_f32: *mut c_void) -> c_int;
         pub fn fb_renderer_create(b: *mut FbBuilder, out: *mut *mut FbRenderer) -> c_int;
         pub fn fb_renderer_destroy(r: *mut FbRenderer);
-        pub fn fb_renderer_draw(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, depth: *const f32,
-                                color: *mut f32, transmittance: *mut f32, w: u32, h: u32, stream: *mut c_void) -> c_int;
+        pub fn fb_renderer_draw(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, depth: *const f32, color_out: *mut f32, transm_out: *mut f32, width: u32, height: u32, stream: *mut c_void) -> c_int;
+        pub fn fb_renderer_draw_blend(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, depth: *const f32, framebuffer_rgba: *mut f32, width: u32, height: u32, stream: *mut c_void) -> c_int;
+        pub fn fb_renderer_draw_sweep(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, views: u32, depth: *const f32, color_out: *mut f32, transm_out: *mut f32, width: u32, height: u32, stream: *mut c_void) -> c_int;
+        pub fn fb_renderer_draw_host(r: *mut FbRenderer, a: *const FbAtmosphere, d: *const FbDrawParams, depth_host: *const f32, color_host: *mut f32, transm_host: *mut f32, width: u32, height: u32) -> c_int;
+        pub fn fb_sky_radiance(a: *const FbAtmosphere, camera: *const f32, view_ray: *const f32, sun_direction: *const f32, n: u64, radiance_out: *mut f32, transmittance_out: *mut f32, stream: *mut c_void) -> c_int;
+        pub fn fb_sun_and_sky_irradiance(a: *const FbAtmosphere, point: *const f32, normal: *const f32, sun_direction: *const f32, n: u64, sun_irradiance_out: *mut f32, sky_irradiance_out: *mut f32, stream: *mut c_void) -> c_int;
+        pub fn fb_atmosphere_build_batch(b: *mut FbBuilder, params: *const FbParams, n: u32, order: u32, stream: *mut c_void, out: *mut *mut FbPending) -> c_int;
+        pub fn fb_sharded_plan(p: *const FbParams, order: u32, rank: c_int, world: c_int, flags: u32, steps: *mut FbShardStep, capacity: u32, count: *mut u32) -> c_int;
+        pub fn fb_atmosphere_build_sharded(b: *mut FbBuilder, p: *const FbParams, order: u32, nccl_comm: *mut c_void, rank: c_int, world: c_int, flags: u32, stream: *mut c_void, out: *mut *mut FbPending) -> c_int;
+        pub fn fb_pending_run_sharded(p: *mut FbPending, nccl_comm: *mut c_void, rank: c_int, world: c_int, flags: u32, stream: *mut c_void) -> c_int;
+        pub fn fb_nccl_version(version: *mut c_int) -> c_int;
+        pub fn fb_nccl_unique_id(id128: *mut c_void) -> c_int;
+        pub fn fb_nccl_comm_create(device: c_int, world: c_int, rank: c_int, id128: *const c_void, nccl_comm_out: *mut *mut c_void) -> c_int;
+        pub fn fb_nccl_comm_destroy(nccl_comm: *mut c_void) -> c_int;
     }
 }
 
@@ -116,9 +188,9 @@ impl Default for Parameters {
 
 impl Parameters {
     /// src/precompute.rs:771-793
-    pub fn transmittance_extent(&self) -> (u32, u32) { (self.transmittance_mu_size, self.transmittance_r_size) }
-    pub fn irradiance_extent(&self) -> (u32, u32) { (self.irradiance_mu_s_size, self.irradiance_r_size) }
-    pub fn scattering_extent(&self) -> (u32, u32, u32) { (self.scattering_nu_size * self.scattering_mu_s_size, self.scattering_mu_size, self.scattering_r_size) }
+    pub fn transmittance_extent(&self) -> vk::Extent2D { vk::Extent2D { width: self.transmittance_mu_size, height: self.transmittance_r_size } }
+    pub fn irradiance_extent(&self) -> vk::Extent2D { vk::Extent2D { width: self.irradiance_mu_s_size, height: self.irradiance_r_size } }
+    pub fn scattering_extent(&self) -> vk::Extent3D { vk::Extent3D { width: self.scattering_nu_size * self.scattering_mu_s_size, height: self.scattering_mu_size, depth: self.scattering_r_size } }
     /// ParamsRaw::new, src/precompute.rs:964-991
     fn raw(&self) -> ffi::FbParams {
         let prof = |p: &DensityProfile| { let mut o = ffi::FbDensityProfile::default(); for i in 0..2 { let l = &p.layers[i];
@@ -138,29 +210,39 @@ impl Parameters {
     }
 }
 
-/// `Builder::new` (src/precompute.rs:61-68): the Vulkan instance/device/cache/queue arguments collapse to a CUDA ordinal.
+/// `Builder::new` (src/precompute.rs:61-68).  The Vulkan instance / device / cache / physical device / queue families
+/// have no CUDA meaning and are ignored; the CUDA device is `$FUZZYBLUE_B200_DEVICE` (default ordinal 0).
 pub struct Builder { raw: *mut ffi::FbBuilder }
 impl Builder {
-    pub fn new(device: i32) -> Self { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::fb_builder_create(device, &mut raw) }); Self { raw } }
+    pub fn new<I, D>(_instance: &I, _device: Arc<D>, _cache: vk::PipelineCache, _physical: vk::PhysicalDevice,
+                     _gfx_queue_family: u32, _compute_queue_family: Option<u32>) -> Self {
+        let ordinal = std::env::var("FUZZYBLUE_B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+        Self::with_cuda_device(ordinal)
+    }
+    /// Not in the reference: pick the CUDA device explicitly.
+    pub fn with_cuda_device(device: i32) -> Self { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::fb_builder_create(device, &mut raw) }); Self { raw } }
 }
 impl Drop for Builder { fn drop(&mut self) { unsafe { ffi::fb_builder_destroy(self.raw) } } }
 
 /// src/precompute.rs:1036-1043
 pub struct Atmosphere { _builder: Arc<Builder>, raw: *const ffi::FbAtmosphere, owned: bool }
 impl Atmosphere {
-    /// `Atmosphere::build(builder, cmd, &params)` (src/precompute.rs:1077-1081): enqueue on `stream`, return at once.
-    pub unsafe fn build(builder: Arc<Builder>, stream: *mut c_void, params: &Parameters) -> PendingAtmosphere {
+    /// `Atmosphere::build(builder, cmd, &params)` (src/precompute.rs:1077-1081): enqueue on the stream `cmd`, return at once.
+    pub unsafe fn build(builder: Arc<Builder>, cmd: vk::CommandBuffer, params: &Parameters) -> PendingAtmosphere {
         let mut raw = std::ptr::null_mut();
-        check(ffi::fb_atmosphere_build(builder.raw, &params.raw(), params.order, stream, &mut raw));
+        check(ffi::fb_atmosphere_build(builder.raw, &params.raw(), params.order, cmd, &mut raw));
         PendingAtmosphere { builder, raw }
     }
-    /// Device pointers to the linear tables (layout: include/fuzzyblue.h) — the `vk::Image` getters of :2075-2101.
+    /// Device pointers to the linear tables (layout: include/fuzzyblue.h) -- the `vk::Image` / `vk::ImageView` getters of :2075-2101.
     pub fn transmittance(&self) -> *const c_void { let mut p = std::ptr::null(); check(unsafe { ffi::fb_atmosphere_transmittance(self.raw, &mut p, std::ptr::null_mut()) }); p }
-    pub fn transmittance_extent(&self) -> (u32, u32) { let mut e = ffi::FbExtent2D::default(); check(unsafe { ffi::fb_atmosphere_transmittance(self.raw, std::ptr::null_mut(), &mut e) }); (e.width, e.height) }
+    pub fn transmittance_view(&self) -> *const c_void { self.transmittance() }
+    pub fn transmittance_extent(&self) -> vk::Extent2D { let mut e = ffi::FbExtent2D::default(); check(unsafe { ffi::fb_atmosphere_transmittance(self.raw, std::ptr::null_mut(), &mut e) }); vk::Extent2D { width: e.width, height: e.height } }
     pub fn scattering(&self) -> *const c_void { let mut p = std::ptr::null(); check(unsafe { ffi::fb_atmosphere_scattering(self.raw, &mut p, std::ptr::null_mut()) }); p }
-    pub fn scattering_extent(&self) -> (u32, u32, u32) { let mut e = ffi::FbExtent3D::default(); check(unsafe { ffi::fb_atmosphere_scattering(self.raw, std::ptr::null_mut(), &mut e) }); (e.width, e.height, e.depth) }
+    pub fn scattering_view(&self) -> *const c_void { self.scattering() }
+    pub fn scattering_extent(&self) -> vk::Extent3D { let mut e = ffi::FbExtent3D::default(); check(unsafe { ffi::fb_atmosphere_scattering(self.raw, std::ptr::null_mut(), &mut e) }); vk::Extent3D { width: e.width, height: e.height, depth: e.depth } }
     pub fn irradiance(&self) -> *const c_void { let mut p = std::ptr::null(); check(unsafe { ffi::fb_atmosphere_irradiance(self.raw, &mut p, std::ptr::null_mut()) }); p }
-    pub fn irradiance_extent(&self) -> (u32, u32) { let mut e = ffi::FbExtent2D::default(); check(unsafe { ffi::fb_atmosphere_irradiance(self.raw, std::ptr::null_mut(), &mut e) }); (e.width, e.height) }
+    pub fn irradiance_view(&self) -> *const c_void { self.irradiance() }
+    pub fn irradiance_extent(&self) -> vk::Extent2D { let mut e = ffi::FbExtent2D::default(); check(unsafe { ffi::fb_atmosphere_irradiance(self.raw, std::ptr::null_mut(), &mut e) }); vk::Extent2D { width: e.width, height: e.height } }
 }
 impl Drop for Atmosphere { fn drop(&mut self) { if self.owned { unsafe { ffi::fb_atmosphere_destroy(self.raw as *mut _) } } } }
 
@@ -168,15 +250,18 @@ impl Drop for Atmosphere { fn drop(&mut self) { if self.owned { unsafe { ffi::fb
 pub struct PendingAtmosphere { builder: Arc<Builder>, raw: *mut ffi::FbPending }
 impl PendingAtmosphere {
     /// Queue-family ownership transfer (:2147-2201) has no CUDA analogue.
-    pub unsafe fn acquire_ownership(&self, _stream: *mut c_void, _compute_queue_family: u32, _gfx_queue_family: u32) {}
+    pub unsafe fn acquire_ownership(&self, _cmd: vk::CommandBuffer, _compute_queue_family: u32, _gfx_queue_family: u32) {}
     pub unsafe fn atmosphere(&self) -> Atmosphere { let mut a = std::ptr::null(); check(ffi::fb_pending_atmosphere(self.raw, &mut a)); Atmosphere { _builder: self.builder.clone(), raw: a, owned: false } }
-    /// Caller asserts the stream has completed (:2208-2211).
+    /// Caller asserts the stream has completed (:2208-2211); as in the reference nothing is verified (check = 0): the
+    /// temporaries are recycled stream-ordered, so even a too-early call cannot corrupt a later precompute.
     pub unsafe fn assert_ready(mut self) -> Atmosphere {
         let mut a = std::ptr::null_mut(); check(ffi::fb_pending_assert_ready(self.raw, 0, &mut a)); self.raw = std::ptr::null_mut();
         Atmosphere { _builder: self.builder.clone(), raw: a, owned: true }
     }
+    /// Not in the reference: block until the precompute has finished (the fence wait of tests/smoke.rs:147-155).
+    pub fn wait(&self) { check(unsafe { ffi::fb_pending_wait(self.raw) }) }
     /// Re-submit the recorded stream (what benches/precompute.rs:138-148 does with its command buffer).
-    pub unsafe fn resubmit(&self, stream: *mut c_void) { check(ffi::fb_pending_resubmit(self.raw, stream)) }
+    pub unsafe fn resubmit(&self, cmd: vk::CommandBuffer) { check(ffi::fb_pending_resubmit(self.raw, cmd)) }
     /// Later `resubmit`s also copy the finished tables to these pinned host buffers (null = keep on the device),
     /// overlapped with the last kernels of the command stream.
     pub unsafe fn set_readback(&self, transmittance: *mut c_void, scattering: *mut c_void, irradiance: *mut c_void) {
@@ -189,16 +274,25 @@ impl Drop for PendingAtmosphere { fn drop(&mut self) { if !self.raw.is_null() { 
 #[derive(Debug, Copy, Clone)]
 pub struct DrawParameters { pub inverse_viewproj: [[f32; 4]; 4], pub camera_position: [f32; 3], pub sun_direction: [f32; 3] }
 
-/// src/render.rs:13-19; render pass / subpass / frame count have no CUDA meaning.
-pub struct Renderer { raw: *mut ffi::FbRenderer, depth: Vec<*const f32> }
+/// src/render.rs:13-19.  Pipeline cache / render pass / subpass have no CUDA meaning; `frames` sizes the per-frame state.
+pub struct Renderer { raw: *mut ffi::FbRenderer, depth: Vec<vk::DescriptorImageInfo>, color: *mut f32, transmittance: *mut f32 }
 impl Renderer {
-    pub fn new(builder: &Builder, frames: u32) -> Self { let mut raw = std::ptr::null_mut(); check(unsafe { ffi::fb_renderer_create(builder.raw, &mut raw) }); Self { raw, depth: vec![std::ptr::null(); frames as usize] } }
-    /// src/render.rs:194-207: the depth attachment of a frame, here a device pointer to `[h][w]` f32.
-    pub unsafe fn set_depth_buffer(&mut self, frame: u32, depth: *const f32) { self.depth[frame as usize] = depth; }
-    /// src/render.rs:209-236 with the two fragment outputs as explicit `[h][w][4]` f32 device buffers.
-    pub fn draw(&self, stream: *mut c_void, atmosphere: &Atmosphere, frame: u32, params: &DrawParameters, color: *mut f32, transmittance: *mut f32, width: u32, height: u32) {
+    /// `Renderer::new(&builder, cache, render_pass, subpass, frames)`, src/render.rs:34-40
+    pub fn new(builder: &Builder, _cache: vk::PipelineCache, _render_pass: vk::RenderPass, _subpass: u32, frames: u32) -> Self {
+        let mut raw = std::ptr::null_mut(); check(unsafe { ffi::fb_renderer_create(builder.raw, &mut raw) });
+        let none = vk::DescriptorImageInfo { depth: std::ptr::null(), width: 0, height: 0 };
+        Self { raw, depth: vec![none; frames as usize], color: std::ptr::null_mut(), transmittance: std::ptr::null_mut() }
+    }
+    /// src/render.rs:194-207: the depth attachment of a frame.
+    pub unsafe fn set_depth_buffer(&mut self, frame: u32, image: &vk::DescriptorImageInfo) { self.depth[frame as usize] = *image; }
+    /// Not in the reference (there the two fragment outputs land in the render pass's colour attachment through the
+    /// dual-source blend, src/render.rs:124-137): `[h][w][4]` f32 device buffers for colour and transmittance.
+    pub unsafe fn set_targets(&mut self, color: *mut f32, transmittance: *mut f32) { self.color = color; self.transmittance = transmittance; }
+    /// `Renderer::draw(&self, cmd, &atmosphere, frame, &params)`, src/render.rs:209-215
+    pub fn draw(&self, cmd: vk::CommandBuffer, atmosphere: &Atmosphere, frame: u32, params: &DrawParameters) {
         let raw = ffi::FbDrawParams { inverse_viewproj: params.inverse_viewproj, camera_position: params.camera_position, _pad: 0, sun_direction: params.sun_direction };
-        check(unsafe { ffi::fb_renderer_draw(self.raw, atmosphere.raw, &raw, self.depth[frame as usize], color, transmittance, width, height, stream) });
+        let d = self.depth[frame as usize];
+        check(unsafe { ffi::fb_renderer_draw(self.raw, atmosphere.raw, &raw, d.depth, self.color, self.transmittance, d.width, d.height, cmd) });
     }
 }
 impl Drop for Renderer { fn drop(&mut self) { unsafe { ffi::fb_renderer_destroy(self.raw) } } }
