@@ -122,9 +122,9 @@ def cpu_precompute_ms():
 
 def ncu_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of k_density_main per launch, from the committed `ncu --set full`
-    capture (profiles/r1_precompute_full_raw.csv); None if the capture is not there."""
+    capture (profiles/r2_precompute_full_raw.csv); None if the capture is not there."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_precompute_full_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r2_precompute_full_raw.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -133,7 +133,7 @@ def ncu_dram_traffic():
         for r in rows[2:]:
             if "k_density_main<0>" in r[name]:    # <0>: the order >= 3 instantiation
                 return (float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]],
-                        "bytes per launch, profiles/r1_precompute_full_raw.csv (order >= 3 launch; tables are L2-resident)")
+                        "bytes per launch, profiles/r2_precompute_full_raw.csv (order >= 3 launch; tables are L2-resident)")
     except (OSError, ValueError, KeyError, IndexError):
         pass
     return (None, "no ncu capture found")
