@@ -29,9 +29,15 @@ struct xf {
     __device__ __forceinline__ xf() {}
     __device__ __forceinline__ constexpr xf(float x) : v(x) {}
 };
+#ifdef FB_XF_CONTRACT_EXPERIMENT   // measurement only: what exactness costs the sky evaluation
+__device__ __forceinline__ xf operator+(xf a, xf b) { return xf(a.v + b.v); }
+__device__ __forceinline__ xf operator-(xf a, xf b) { return xf(a.v - b.v); }
+__device__ __forceinline__ xf operator*(xf a, xf b) { return xf(a.v * b.v); }
+#else
 __device__ __forceinline__ xf operator+(xf a, xf b) { return xf(__fadd_rn(a.v, b.v)); }
 __device__ __forceinline__ xf operator-(xf a, xf b) { return xf(__fsub_rn(a.v, b.v)); }
 __device__ __forceinline__ xf operator*(xf a, xf b) { return xf(__fmul_rn(a.v, b.v)); }
+#endif
 __device__ __forceinline__ xf operator/(xf a, xf b) { return xf(__fdiv_rn(a.v, b.v)); }
 __device__ __forceinline__ xf operator-(xf a) { return xf(-a.v); }
 __device__ __forceinline__ xf& operator+=(xf& a, xf b) { a = a + b; return a; }

@@ -6,7 +6,7 @@ make -s -j4
 mkdir -p ../../build/variants
 HOSTCXX=$(command -v /usr/bin/g++ || echo g++)
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin $HOSTCXX -O3 -std=c++17 -lineinfo \
-  -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off --expt-relaxed-constexpr $2 -c fb_render.cu -o ../../build/variants/$1.o
+  -Xcompiler -fPIC,-fvisibility=hidden,-ffp-contract=off --expt-relaxed-constexpr $2 $3 -c fb_render.cu -o ../../build/variants/$1.o
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin $HOSTCXX -shared -o ../../build/variants/$1.so \
-  fb_api.o fb_kernels_ref.o fb_kernels_fast.o ../../build/variants/$1.o fb_peak.o -cudart static
+  fb_api.o fb_sharded.o fb_kernels_ref.o fb_kernels_fast.o ../../build/variants/$1.o fb_peak.o -cudart static -ldl
 echo built build/variants/$1.so
