@@ -109,7 +109,8 @@ template <bool ORDER2> struct DensityCfg {
     static constexpr int NWARPS = 8;
 };
 struct DensityDims {
-    int nu, ms_tile, tiles, ms_shift;   // ms_tile = T / nu mu_s columns per CTA; ms_shift = log2(ms_tile), or -1 when it is not a power of two
+    int nu, ms_tile, tiles;             // ms_tile = T / nu mu_s columns per CTA (any nu: 3, 6, 12 ... need not be a power of two)
+    uint32_t ms_mul;                    // ceil(2^20 / ms_tile): t / ms_tile == (t * ms_mul) >> 20 for every texel index t < 256
 };
 // what the restructured density kernels cover: a CTA needs at least one whole mu_s column (nu <= 128 texels at order 2) and
 // the eight ground rows must fit beside the table slice.  Anything else runs the one-thread-per-texel transcription, ~30x
@@ -123,9 +124,7 @@ static inline DensityDims density_dims(const FbParams& P, int T) {
     DensityDims d;
     d.nu = P.scattering_nu_size;
     d.ms_tile = T / d.nu;
-    d.ms_shift = 0;
-    while ((1 << d.ms_shift) < d.ms_tile) ++d.ms_shift;
-    if ((1 << d.ms_shift) != d.ms_tile) d.ms_shift = -1;   // nu = 3, 6, 12 ...: texel <-> (nu slice, mu_s column) by division
+    d.ms_mul = d.ms_tile > 0 ? (uint32_t)(((1u << 20) + d.ms_tile - 1) / d.ms_tile) : 0u;   // exact while t * ms_tile < 2^20
     d.tiles = (P.scattering_mu_s_size + d.ms_tile - 1) / d.ms_tile;
     return d;
 }
@@ -308,7 +307,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     F r, mu;
     {
         const int t = tid < TT ? tid : 0;
-        const int nui = dd.ms_shift >= 0 ? t >> dd.ms_shift : t / dd.ms_tile, msl = t - nui * dd.ms_tile;
+        const int nui = (int)(((uint32_t)t * dd.ms_mul) >> 20), msl = t - nui * dd.ms_tile;
         const int ms = tile * dd.ms_tile + msl;
         const bool valid = tid < TT && nui < dd.nu && ms < P.scattering_mu_s_size;   // nui >= nu: padding of a tile with T % nu != 0
         F mu_s, nu;
@@ -445,19 +444,19 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     // one does).  The two patterns an Earth-like shell produces are compiled with L0 fixed: the 16 unrolled steps then
     // form one basic block and the loads of later steps are scheduled across the ground terms of earlier ones.  Any
     // other pattern takes the L0 = -1 body, which tests the mask per step.
-    auto store = [&](int rec, float ar, float ag, float ab) {                 // the texel and its followers
+    // The texel and its followers (the next nu slices): every lane of the group holds the sums after the butterfly, so
+    // lane `sub` of `group` writes follower sub, sub + group, ... -- one predicated store instead of a serial loop.
+    auto store = [&](int rec, float ar, float ag, float ab, int sub, int group) {
         const uint2 v = pack_half4(ar, ag, ab, 0.f);
         const int t = (rec >> 14) & 0xff;
-        const int tn = dd.ms_shift >= 0 ? t >> dd.ms_shift : t / dd.ms_tile;
+        const int tn = (int)(((uint32_t)t * dd.ms_mul) >> 20);
         uint2* o = out + (out_row + tn * P.scattering_mu_s_size + tile * dd.ms_tile + (t - tn * dd.ms_tile));
-#pragma unroll 1
-        for (int nf = rec >> 22; nf >= 0; --nf, o += P.scattering_mu_s_size) *o = v;   // followers: the next nu slices
+        for (int k = sub, nf = rec >> 22; k <= nf; k += group) o[(size_t)k * P.scattering_mu_s_size] = v;
     };
     auto texels = [&](auto L0c) __attribute__((always_inline)) {
     constexpr int L0 = decltype(L0c)::value;
-#pragma unroll 2
-    for (int i = warp; i < nGen; i += NWARPS) {
-        const float4 geo = geoS[i];
+    // the 512 samples of one texel: lane = phi sample, 16 unrolled theta rows; per-lane partial sums come back in (ar, ag, ab)
+    auto texel_sums = [&](const float4 geo, float& ar, float& ag, float& ab) __attribute__((always_inline)) {
         // w_s . w_i = sin(theta_l) * q + mu_s * cos(theta_l) with q = sx cos(phi) + sy sin(phi) per (texel, lane).
         // |w_s . w_i| <= sqrt(q^2 + mu_s^2) for every theta; pull (q, mu_s) inside the unit disc by a hair so that
         // neither the nu look-up below nor the ground look-up can step outside its table row — no per-sample clamps.
@@ -469,7 +468,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         }
         if (!ORDER2) { q *= hn; mus *= hn; }                                      // tcx = hn * nu1 + hn in two FFMAs
         const uint32_t row_t = tab_base + ((uint32_t)__float_as_int(geo.w) & 0x3fffu);
-        float ar = 0.f, ag = 0.f, ab = 0.f;
+        ar = 0.f; ag = 0.f; ab = 0.f;
 #define FB_DENSITY_STEP(l)                                                                                              \
         {                                                                                                               \
             float nu1, tcx;                                                       /* scattering.h:146, in [0, nu-1) */  \
@@ -512,13 +511,28 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         FB_DENSITY_STEP(8) FB_DENSITY_STEP(9) FB_DENSITY_STEP(10) FB_DENSITY_STEP(11)
         FB_DENSITY_STEP(12) FB_DENSITY_STEP(13) FB_DENSITY_STEP(14) FB_DENSITY_STEP(15)
 #undef FB_DENSITY_STEP
+    };
+    // Two texels per iteration: their partial sums meet in ONE butterfly -- the first exchange hands texel 0 to lanes 0-15
+    // and texel 1 to lanes 16-31 (3 shuffles for both texels instead of 6), the remaining four steps run on half-warps.
+    // Each texel's sum is associated exactly as by a full-warp butterfly of its own (lane l + lane l ^ 16 first).
+    for (int i = warp; i < nGen; i += 2 * NWARPS) {
+        const bool two = i + NWARPS < nGen;                                       // warp-uniform
+        const float4 geo0 = geoS[i], geo1 = geoS[two ? i + NWARPS : i];
+        float a0r, a0g, a0b, a1r = 0.f, a1g = 0.f, a1b = 0.f;
+        texel_sums(geo0, a0r, a0g, a0b);
+        if (two) texel_sums(geo1, a1r, a1g, a1b);
+        const bool up = lane >= 16;
+        float ar = up ? a1r : a0r, ag = up ? a1g : a0g, ab = up ? a1b : a0b;      // what this half-warp keeps
+        ar += __shfl_xor_sync(0xffffffffu, up ? a0r : a1r, 16);
+        ag += __shfl_xor_sync(0xffffffffu, up ? a0g : a1g, 16);
+        ab += __shfl_xor_sync(0xffffffffu, up ? a0b : a1b, 16);
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
+        for (int s = 8; s > 0; s >>= 1) {
             ar += __shfl_xor_sync(0xffffffffu, ar, s);
             ag += __shfl_xor_sync(0xffffffffu, ag, s);
             ab += __shfl_xor_sync(0xffffffffu, ab, s);
         }
-        if (lane == 0) store(__float_as_int(geo.w), ar, ag, ab);
+        if (!up || two) store(__float_as_int(up ? geo1.w : geo0.w), ar, ag, ab, lane & 15, 16);
     }
     // ---- paired body: two texels per warp (lanes 0-15 / 16-31), a lane takes the mirror samples phi_m and 2 pi - phi_m
     // (same cos phi, hence the same phase weight; sin phi flips).  With sy ~ 0 both fall into the same table segment
@@ -658,7 +672,7 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             ag += __shfl_xor_sync(0xffffffffu, ag, s);
             ab += __shfl_xor_sync(0xffffffffu, ab, s);
         }
-        if ((lane & 15) == 0 && valid) store(__float_as_int(geo.w), ar, ag, ab);
+        if (valid) store(__float_as_int(geo.w), ar, ag, ab, lane & 15, 16);
     }
     };
     if (gmask == 0xFF00u) texels(std::integral_constant<int, 8>());
