@@ -95,7 +95,7 @@ def test_non_multiple_of_workgroup_dims_are_fully_written():
         assert np.max(np.abs(Tf - ref.transmittance) / ref.transmittance) <= 1e-3
         assert np.max(np.abs(Ef - ref.irradiance) / np.maximum(ref.irradiance, 1e-30)) <= 1e-3
         e = np.abs(Sf.astype(np.float64) - ref.scattering) / np.maximum(np.abs(ref.scattering), 2.0 ** -14)
-        assert (e > 1e-3).sum() <= 8 and e.max() <= 4e-2, (d, e.max(), int((e > 1e-3).sum()))   # the end-to-end gate of test_parity_gpu.check_compounded
+        assert (e > 1e-3).sum() <= 8 and e.max() <= 2e-2, (d, e.max(), int((e > 1e-3).sum()))   # the end-to-end gate of test_parity_gpu.check_compounded
 
 
 def test_exported_allocation_carries_the_tables():

@@ -56,13 +56,14 @@ def check_compounded(name, e, max_count=None):
     fp32 oracle: the FINAL scattering table has 60 of 4 194 304 values (1.4e-5) beyond 1e-3, maximum 9.2e-3; the worst
     intermediate is the order-4 delta_multiple_scattering with 388 values (9.3e-5), maximum 1.28e-2 (1.33e-2 in the
     order-2 scattering table); the contraction-free family, which differs from the oracle only by expf / powf ulps,
-    shows up to 27 values and 4.4e-3.   ->  fraction <= 3e-4, maximum <= 4e-2 (round 1 accepted 2e-3 and 2e-2).
+    shows up to 27 values and 4.4e-3.   ->  fraction <= 3e-4 (3x; round 1 accepted 2e-3), maximum <= 2e-2 (1.5x: the kernels
+    are run-to-run identical, so the margin only has to absorb another driver's expf; round 1 accepted the same).
     Small tables get an absolute allowance (`max_count` values): one value of a 4096-texel table is already 6e-5 of it."""
     n_out = int((e > RTOL).sum())
     frac = n_out / e.size
     print(f"{name}: max {e.max():.3e}, beyond 1e-3: {n_out} of {e.size} values ({frac:.2e})")
     allowed = max(int(3e-4 * e.size), 0 if max_count is None else max_count)
-    assert n_out <= allowed and e.max() <= 4e-2, f"{name}: max {e.max():.3e}, {n_out} values beyond 1e-3 (allowed {allowed})"
+    assert n_out <= allowed and e.max() <= 2e-2, f"{name}: max {e.max():.3e}, {n_out} values beyond 1e-3 (allowed {allowed})"
 
 
 @pytest.fixture(scope="module", params=list(FAMILIES))
