@@ -14,6 +14,7 @@ SURVEY.md §8e) and `value` is the time per atmosphere over the whole job: weak 
 Prints ONE JSON line (rank 0).  Extra objects, at every N:
   `render`  the second half of BASELINE.json's metric: sky evaluation Mpixel/s at 3840x2160 over the 256-view sweep
             (configs[4]); at N > 1 the views are split rank::N, the 8.25 MiB tables are built per rank, no collective;
+  `batch`   BASELINE.json configs[3]: 1024 distinct atmospheres (fresh builds, allocation included) split over the ranks;
   `hires`   BASELINE.json configs[2]: ONE high-resolution atmosphere (2 GiB per 3-D table, 8 orders) built by all N
             ranks through fb_pending_run_sharded -- the configuration that communicates (one all-gather of
             scattering_density per order, one-slice halos, irradiance rows over NCCL): strong scaling, with the bytes;
@@ -299,6 +300,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     render = None if args.no_render else render_leg(args, builder, pending, stream, dev, rank, world, fma_tflops, sfu_gops)
     del flush_buf
     hires = None if args.no_hires else hires_leg(args, builder, rank, local_rank, world, dev)
+    batch = None if args.no_batch else batch_leg(args, builder, rank, local_rank, world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,6 +361,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                           "roofline_bound": (render["roofline"] or {}).get("bound"),
                           "e2e_mpixel_s": render["e2e"]["value"], "e2e_h2d_bytes": render["e2e"]["h2d_bytes_per_step"],
                           "e2e_d2h_bytes": render["e2e"]["d2h_bytes_per_step"]}
+    if batch:
+        legs["batch"] = {"metric": batch["metric"], "ms_per_atmosphere": batch["value"], "atmospheres": args.batch_atmospheres,
+                         "n_gpus": batch["n_gpus"], "scaling": "strong", "atmospheres_per_second": batch["atmospheres_per_second"]}
     if hires:
         legs["hires"] = {"metric": hires["metric"], "ms": hires["value"], "n_gpus": hires["n_gpus"], "scaling": "strong",
                          "bytes_received_per_rank": hires["collective"]["bytes_received_per_rank_per_step"],
@@ -373,7 +378,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                     "note": "one graph replay that carries the precompute and the read-back of transmittance, scattering, irradiance into "
                             "pinned host memory (fb_pending_set_readback), host wall clock from submit to stream sync"},
             "gpu_launches": launches * args.steps, "launches_per_step": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "render": render, "hires": hires}
+            "cpu_baseline": cpu, "render": render, "hires": hires, "batch": batch}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -471,23 +476,18 @@ def run_hires(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
-def run_batch(args, rank: int, local_rank: int, world: int):
-    """--workload batch: BASELINE.json configs[3] — 1024 distinct atmospheres (randomised Rayleigh / Mie / ozone, Earth-to-Mars
-    radii, default dims, 4 orders) sharded across the ranks with no communication.  Every atmosphere is a FRESH
+def batch_leg(args, builder, rank: int, local_rank: int, world: int, dev):
+    """BASELINE.json configs[3] -- 1024 distinct atmospheres (randomised Rayleigh / Mie / ozone, Earth-to-Mars radii,
+    default dims, 4 orders) sharded across the ranks with no communication.  Every atmosphere is a FRESH
     fb_atmosphere_build (allocation included, served from the builder's block cache), 32 in flight per GPU on forked
-    streams; the 1024 result sets stay resident in HBM (8.3 MiB each)."""
+    streams; a rank's result sets stay resident in HBM (8.3 MiB each) until the pass is over.  Returns the record on rank 0."""
     import torch
     import torch.distributed as dist
 
     import fuzzyblue_b200 as fb
     from fuzzyblue_b200 import synthetic
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     total = args.batch_atmospheres
     mine = synthetic.random_atmospheres(total, seed=20260)[rank::world]
-    builder = fb.Builder(local_rank)
     stream = torch.cuda.Stream(device=dev)
     CH = 32
 
@@ -508,8 +508,8 @@ def run_batch(args, rank: int, local_rank: int, world: int):
 
     for a in one_pass(mine[:CH]):      # warm-up: module load, block cache
         a.close()
-    times, launches = [], 0
-    for _ in range(args.steps):
+    times, finite = [], True
+    for _ in range(max(1, args.batch_steps)):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -517,21 +517,38 @@ def run_batch(args, rank: int, local_rank: int, world: int):
         atms = one_pass(mine)
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
-        finite = all(bool(torch.isfinite(torch.tensor(a.read_irradiance())).all()) for a in atms[:4])
+        finite = finite and all(bool(torch.isfinite(torch.tensor(a.read_irradiance())).all()) for a in atms[:4])
         for a in atms:
             a.close()
+    builder.trim()
     t = torch.tensor([sum(times)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    sec = float(t.item()) / len(times)
+    return {"metric": "LUT precompute ms per atmosphere (4 orders, default dims, batch of distinct atmospheres)",
+            "value": sec * 1e3 / total, "unit": "ms", "n_gpus": world, "steps": len(times), "warmup": 1,
+            "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{total} distinct atmospheres (BASELINE.json configs[3]), {len(mine)} per GPU, 32 in flight",
+                       "timing": "wall clock around the whole pass incl. allocation, max over ranks", "kernels": "FAST"},
+            "atmospheres_per_second": total / sec, "results_finite": finite, "gpu_launches": 16 * len(mine) * len(times)}
+
+
+def run_batch(args, rank: int, local_rank: int, world: int):
+    """--workload batch: the `batch` leg alone, as the run's one JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    import fuzzyblue_b200 as fb
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.batch_steps = args.steps
+    line = batch_leg(args, fb.Builder(local_rank), rank, local_rank, world, dev)
     if rank == 0:
-        sec = float(t.item()) / args.steps
-        line = {"metric": "LUT precompute ms per atmosphere (4 orders, default dims, batch of distinct atmospheres)",
-                "value": sec * 1e3 / total, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": 1,
-                "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": f"{total} distinct atmospheres (BASELINE.json configs[3]), {len(mine)} per GPU, 32 in flight",
-                           "timing": "wall clock around the whole pass incl. allocation, max over ranks", "kernels": "FAST"},
-                "atmospheres_per_second": total / sec, "results_finite": finite, "gpu_launches": 16 * len(mine) * args.steps}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -675,6 +692,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-hires", action="store_true")
+    ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--batch-steps", type=int, default=1)
     ap.add_argument("--hires-steps", type=int, default=2)
     ap.add_argument("--workload", default="default", choices=["default", "hires", "batch"])
     ap.add_argument("--batch-atmospheres", type=int, default=1024)
