@@ -103,22 +103,30 @@ def cpu_model() -> str:
     return "unknown"
 
 
-def cpu_precompute_ms():
-    """ONE full default-dims 4-order precompute on the CPU oracle (fp32 mode = the shaders as written): real tables,
-    every texel of every stage, OpenMP over all host cores.  A measurement, not an extrapolation."""
+def cpu_precompute_ms(prefer_reference: bool = True):
+    """ONE full default-dims 4-order precompute on the host cores: real tables, every texel of every stage, OpenMP over
+    all cores.  A measurement, not an extrapolation.  Runs THE REFERENCE'S OWN SHADERS compiled as C++
+    (oracle/_ref/libfb_glsl_ref.so, kind "reference") when that library was built (it needs the reference checkout at
+    build time and travels with the snapshot), else the oracle port (kind "port").  Returns (ms, sample text, kind)."""
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core.  libgomp reads
-    # the variable when the oracle library is first loaded.
+    # the variable when the first OpenMP library is loaded.
     if "oracle.oracle" not in sys.modules:
         os.environ["OMP_NUM_THREADS"] = str(host_cores())
     from oracle import oracle as O
+    from oracle import ref_glsl as R
+    use_ref = prefer_reference and R.available()
+    if use_ref:
+        R.set_threads(host_cores())
     O.set_threads(host_cores())
     t0 = time.perf_counter()
-    tables = O.precompute(O.Params(), O.F32)
+    tables = R.precompute(O.Params()) if use_ref else O.precompute(O.Params(), O.F32)
     dt = time.perf_counter() - t0
     ok = bool((tables.scattering[..., :3] >= 0).all()) and float(tables.irradiance.max()) > 0
-    sample = (f"oracle fp32 port (not lavapipe): one FULL default-dims 4-order precompute, every texel of every stage, "
+    what = ("the reference's own GLSL shaders compiled as C++ (oracle/glsl_ref; not lavapipe)" if use_ref
+            else "oracle fp32 port (not lavapipe)")
+    sample = (f"{what}: one FULL default-dims 4-order precompute, every texel of every stage, "
               f"{dt:.1f} s wall on {host_cores()} cores ({cpu_model()}); result sane: {ok}")
-    return dt * 1e3, sample
+    return dt * 1e3, sample, ("reference" if use_ref else "port")
 
 
 def ncu_dram_traffic():
@@ -168,10 +176,12 @@ def host_cores() -> int:
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's algorithm on the host cores.  The reference itself (Rust + GLSL on Vulkan)
-    cannot run here -- no cargo, no shaderc, no Vulkan loader/ICD (lavapipe or NVIDIA) in the image -- so this arm
-    times the oracle port, OpenMP over all host cores.  Every step is one FULL default-dims 4-order precompute (real
-    tables, every texel); as many of the requested steps run as fit in ~100 s, and `steps` reports what ran."""
+    """--impl reference: the reference's own CPU-runnable implementation of the path on the host cores.  The crate itself
+    (Rust + GLSL on Vulkan) cannot run here -- no cargo, no shaderc, no Vulkan loader/ICD (lavapipe or NVIDIA) in the
+    image -- but its SHADERS can: oracle/_ref/libfb_glsl_ref.so is /root/reference/shaders compiled as C++ (kind
+    "reference"); the oracle port (kind "port") is the fall-back where that library was not built.  OpenMP over all host
+    cores.  Every step is one FULL default-dims 4-order precompute (real tables, every texel); as many of the
+    requested steps run as fit in ~100 s, and `steps` reports what ran."""
     if rank != 0:
         return
     budget_s = 100.0
@@ -184,7 +194,7 @@ def run_reference(args, rank: int):
         spent = time.perf_counter() - t_start
         if len(runs) > warm and spent + spent / len(runs) > budget_s:
             break
-        ms, sample = cpu_precompute_ms()
+        ms, sample, kind = cpu_precompute_ms()
         runs.append(ms)
         if len(runs) == 1 and warm and ms > 30e3:
             warm = 0                       # few host cores: a pass this long is its own warm-up, keep it as a timed step
@@ -194,11 +204,12 @@ def run_reference(args, rank: int):
             "warmup": warm, "requested": {"steps": args.steps, "warmup": args.warmup}, "ms_per_step": v,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores(), "cpu": cpu_model(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_cores(), "cpu": cpu_model(), "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
-            "reference_unavailable": "Rust+GLSL/Vulkan reference cannot be built or run in this image (no cargo, shaderc, "
-                                     "Vulkan loader or ICD); lavapipe and B200-Vulkan baselines are unavailable"}
+            "reference_unavailable": "the Rust crate and its Vulkan pipeline cannot be built or run in this image (no cargo, "
+                                     "shaderc, Vulkan loader or ICD): lavapipe and B200-Vulkan baselines are unavailable; "
+                                     "kind=reference means the crate's own GLSL shaders compiled as C++ and run on the host cores"}
     emit(line)
 
 
@@ -349,8 +360,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sample = cpu_precompute_ms()
-        cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "cpu": cpu_model(), "kind": "port", "sample": sample}
+        v, sample, kind = cpu_precompute_ms()
+        cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "cpu": cpu_model(), "kind": kind, "sample": sample}
 
     # the driver's record keeps `config`, `roofline`, `e2e`, `cpu_baseline` of this line and only the NAMES of other
     # keys: the two extra legs are summarised inside `config` (and carried in full under `render` / `hires`)

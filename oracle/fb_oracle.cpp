@@ -5,10 +5,17 @@
 // legs as the *checker* and the *CPU baseline*.  The shipped path (fuzzyblue_b200/) never
 // links, loads or calls it.
 //
-// PARITY UNPINNED: the reference has no golden vectors, no known-answer tests and cannot be
-// built in this image (no cargo / shaderc / Vulkan ICD), so this file is pinned only by the
-// closed-form identities in tests/test_oracle_kat.py and cross-checked, stage by stage, against
-// an independent scalar numpy restatement of the same shaders (oracle/numpy_check.py, tests/test_oracle_numpy.py).
+// PARITY PIN: the reference has no golden vectors or known-answer tests of its own, and the crate cannot be built
+// in this image (no cargo / shaderc / Vulkan ICD) -- but its SHADERS can be run: oracle/glsl_ref compiles
+// /root/reference/shaders/*.h, *.comp and render_sky.frag as C++ (a GLSL-subset header + a purely syntactic
+// translator) into oracle/_ref/libfb_glsl_ref.so, and mode 0 of this file reproduces the output of that library BIT FOR
+// BIT for every stage, the whole per-order schedule and the sky evaluation (tests/test_reference_glsl.py; the same pin
+// as committed golden vectors generated from the reference's shaders: tests/golden/reference_*.npz,
+// tests/test_golden_cpu.py).  What both sides share by construction is what Vulkan leaves to the driver: binary32
+// arithmetic with the C library's exp / pow / sin / cos, the LINEAR / CLAMP_TO_EDGE sampler with exact weights, and
+// round-to-nearest-even binary16 image stores.  Independently of the reference it is pinned by closed-form
+// known-answer tests for all six stages (tests/test_oracle_kat.py, tests/test_kat_3d.py) and cross-checked against a
+// second scalar numpy restatement (oracle/numpy_check.py, tests/test_oracle_numpy.py).
 //
 // Every routine restates one GLSL function of /root/reference/shaders (cited per function
 // as file:line) in a scalar type R chosen by the caller:

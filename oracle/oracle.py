@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY — imported by ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``; never by ``fuzzyblue_b200``.
-PARITY UNPINNED (see the header of ``fb_oracle.cpp``): the reference ships no golden vectors.
+PARITY PIN (see the header of ``fb_oracle.cpp``): mode 0 reproduces, bit for bit, the reference's own shaders compiled
+as C++ and run on the CPU (``oracle/ref_glsl.py``) and the golden vectors generated from them (``tests/golden/``).
 
 Modes: 0 = fp32 arithmetic, reference storage formats ("the shaders as written");
        1 = fp64 arithmetic, reference storage formats; 2 = fp64, no quantisation.

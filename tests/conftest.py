@@ -75,7 +75,9 @@ def oracle_wide_f32():
 @pytest.fixture(scope="session")
 def oracle_smoke_f32():
     from oracle import oracle as O
-    return O.precompute(O.Params(**SMOKE_DIMS), O.F32, keep_history=True)
+    t = O.precompute(O.Params(**SMOKE_DIMS), O.F32, keep_history=True)
+    assert_equals_reference_golden(t, "reference_smoke_f32.npz")
+    return t
 
 
 @pytest.fixture(scope="session")
@@ -84,9 +86,36 @@ def oracle_dump_f32():
     return O.precompute(O.Params(**DUMP_DIMS), O.F32, keep_history=True)
 
 
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def assert_equals_reference_golden(tables, fixture: str):
+    """`tables` (an oracle run with history) must reproduce, bit for bit, the golden vectors the REFERENCE'S OWN SHADERS
+    produced (tests/golden/make_reference_golden.py): whole tables where the fixture holds them, the seeded texels
+    otherwise.  Every expectation the GPU tests derive from the oracle is thereby the reference's own output."""
+    import numpy as np
+    g = np.load(os.path.join(GOLDEN_DIR, fixture))
+    idx = g["idx"] if "idx" in g.files else None
+    pick = (lambda a: a) if idx is None else (lambda a: a.reshape(-1, 4)[idx])
+    assert np.array_equal(tables.transmittance.astype(np.float32), g["transmittance"])
+    assert np.array_equal(tables.irradiance.astype(np.float32), g["irradiance"])
+    assert np.array_equal(pick(tables.scattering).astype(np.float16), g["scattering"])
+    assert np.array_equal(pick(tables.delta_rayleigh).astype(np.float16), g["delta_rayleigh"])
+    assert np.array_equal(pick(tables.delta_mie).astype(np.float16), g["delta_mie"])
+    for order in (2, 3, 4):
+        h = tables.history[order]
+        for k in ("scattering_density", "delta_multiple_scattering", "scattering"):
+            assert np.array_equal(pick(h[k]).astype(np.float16), g[f"o{order}_{k}"]), (fixture, order, k)
+        for k in ("delta_irradiance", "irradiance"):
+            assert np.array_equal(h[k].astype(np.float32), g[f"o{order}_{k}"]), (fixture, order, k)
+
+
 @pytest.fixture(scope="session")
 def oracle_default_f32():
     """BASELINE.json configs[1] in full: the fp32 oracle's 4-order precompute at the default dims with every intermediate
-    image of every order (15-40 s on the GPU box's host cores; used by the -m gpu parity tests only)."""
+    image of every order (15-40 s on the GPU box's host cores; used by the -m gpu parity tests only).  Checked against
+    the reference's own golden vectors before any kernel is compared with it."""
     from oracle import oracle as O
-    return O.precompute(O.Params(), O.F32, keep_history=True)
+    t = O.precompute(O.Params(), O.F32, keep_history=True)
+    assert_equals_reference_golden(t, "reference_default_f32.npz")
+    return t

@@ -407,6 +407,28 @@ def test_default_dims_stagewise_against_oracle_every_texel(builder, oracle_defau
         check(f"default scattering(order {o})", err16(pend.download(api.IMAGE_SCATTERING), ref.history[o]["scattering"]))
 
 
+def test_cuda_against_the_reference_golden_vectors(default_tables, builder, family):
+    """The CUDA tables against the outputs of the REFERENCE'S OWN SHADERS directly (tests/golden/reference_*.npz, generated
+    by running /root/reference/shaders on the CPU): smoke dims in full, default dims on the 4096 seeded texels of
+    every table of every order and the 2-D tables in full.  Same tolerances as against the oracle (which reproduces
+    these vectors bit for bit, tests/test_golden_cpu.py)."""
+    g = np.load(os.path.join(GOLDEN, "reference_smoke_f32.npz"))
+    T, S, E = fb.precompute_host(builder, fb.Parameters(**SMOKE_DIMS))
+    check("smoke transmittance vs reference", err32(T, g["transmittance"]))
+    check("smoke irradiance vs reference", err32(E, g["irradiance"]))
+    check_compounded("smoke scattering vs reference", err16(S, g["scattering"]), max_count=SMALL_TABLE_OUTLIERS)
+    g = np.load(os.path.join(GOLDEN, "reference_default_f32.npz"))
+    idx = g["idx"]
+    for name in ("transmittance", "irradiance", "direct_irradiance", "o2_delta_irradiance", "o3_delta_irradiance", "o4_delta_irradiance",
+                 "o2_irradiance", "o3_irradiance"):
+        check(name + " vs reference", err32(default_tables[name], g[name]))
+    for name in ("delta_rayleigh", "delta_mie", "o2_scattering_density"):
+        check(name + " vs reference", err16(default_tables[name].reshape(-1, 4)[idx], g[name]))
+    for name in ("o3_scattering_density", "o4_scattering_density", "o2_delta_multiple_scattering", "o3_delta_multiple_scattering",
+                 "o4_delta_multiple_scattering", "o2_scattering", "o3_scattering", "scattering"):
+        check_compounded(name + " vs reference", err16(default_tables[name].reshape(-1, 4)[idx], g[name]), max_count=SMALL_TABLE_OUTLIERS)
+
+
 def test_default_dims_properties(default_tables):
     """Size-independent properties at the full default dims (BASELINE.json configs[1])."""
     T, E = default_tables["transmittance"], default_tables["irradiance"]

@@ -282,3 +282,37 @@ def test_4k_sweep_views_match_oracle_on_default_tables(default_scene):
         n_ground += int(ground.sum())
         n_sky += int((~ground).sum())
     assert n_space >= 6 and n_ground > 100000 and n_sky > 100000
+
+
+def test_draw_on_the_reference_tables_matches_the_reference_rendering():
+    """Golden vectors of the sky evaluation: three views rendered by the REFERENCE'S OWN render_sky.frag (run on the CPU,
+    tests/golden/make_reference_golden.py) from the reference's own tables at the smoke dims.  The tables are uploaded
+    into an atmosphere and drawn by the CUDA renderer: same pixels within 1e-3 (floors as in the 4K test)."""
+    import os
+    import torch
+    from .conftest import SMOKE_DIMS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_smoke_f32.npz"))
+    for kernels in (api.KERNELS_FAST, api.KERNELS_REFERENCE):
+        b = fb.Builder(0, kernels=kernels)
+        pend = fb.Atmosphere.allocate(b, fb.Parameters(**SMOKE_DIMS))
+        pend.upload(api.IMAGE_TRANSMITTANCE, g["transmittance"])
+        pend.upload(api.IMAGE_SCATTERING, g["scattering"])
+        pend.upload(api.IMAGE_IRRADIANCE, g["irradiance"])
+        torch.cuda.synchronize()
+        atm = pend.atmosphere()
+        r = fb.Renderer(b)
+        Wv, Hv = 48, 27
+        draws, extra = synthetic.camera_sweep(24, Wv, Hv)
+        for k in sorted(int(n[4:-6]) for n in g.files if n.startswith("view") and n.endswith("_color")):
+            depth = synthetic.analytic_depth(extra[k][0], extra[k][1], Wv, Hv)
+            color, transm = r.draw_host(atm, draws[k], depth)
+            oc, ot = g[f"view{k}_color"].astype(np.float64), g[f"view{k}_transmittance"].astype(np.float64)
+            undefined = ~np.isfinite(ot)               # the shader's own inf - inf on downward sky rays
+            ot = np.where(undefined, transm, ot)
+            peak = max(float(np.abs(oc).max()), 1e-3)
+            ground = (depth > 0)[..., None]
+            floor = np.where(ground, 1e-3 * peak, 1e-5 * peak)
+            ec = np.abs(color - oc) / np.maximum(np.abs(oc), floor)
+            et = np.abs(transm - ot) / np.maximum(np.abs(ot), 1e-6)
+            print(f"reference view {k} (kernels {kernels}): colour err max {ec.max():.2e}, transmittance err max {et.max():.2e}")
+            assert ec.max() <= 1e-3 and et.max() <= 1e-3, (k, kernels, float(ec.max()), float(et.max()))
