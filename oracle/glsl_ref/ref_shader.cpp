@@ -1,5 +1,5 @@
 // ref_shader.cpp — one translation unit per shader of the reference (compile with -DSHADER_<NAME>): includes the
-// reference's own (syntax-translated) source from oracle/_ref/gen and runs its main() over a dispatch on the CPU.
+// reference's own (syntax-translated) source from the build-time scratch directory and runs its main() over a dispatch on the CPU.
 // TEST INFRASTRUCTURE ONLY; see glsl_compat.h for what is the reference's and what is the "driver" defined here.
 #include <cstdint>
 #include <cstring>

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Rewrites the GLSL syntax of the reference's shader sources that is not C++ (nothing else), so that g++ can compile
-them against glsl_compat.h.  Reads /root/reference/shaders/*, writes oracle/_ref/gen/* (git-ignored build output:
+them against glsl_compat.h.  Reads /root/reference/shaders/*, writes a build-time scratch directory (removed after the build:
 reference sources never enter the repository).
 
     translate.py SHADER_DIR OUT_DIR
