@@ -26,7 +26,7 @@ DIMS = dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=4, s
 
 
 class OracleBackend:
-    """Same interface as sharded.PendingBackend, stages evaluated by the CPU oracle on this rank's slab only."""
+    """What sharded.GlooExecutor drives: run_stage(stage, order, begin, end) evaluated by the CPU oracle, tensor(image) = the whole image."""
 
     def __init__(self, p: O.Params):
         self.p = p
