@@ -180,7 +180,7 @@ int make_plan(const FbParams& P, uint32_t order, int rank, int world, uint32_t f
     int chunks = 1;
     if (multi && !(flags & FB_SHARD_NO_PIPELINE))
         for (int c = std::min(4, n); c >= 1; --c)
-            if (n % c == 0 && (size_t)(n / c) * slice >= ((size_t)16 << 20)) { chunks = c; break; }
+            if (n % c == 0 && ((flags & FB_SHARD_PIPELINE_ALWAYS) || (size_t)(n / c) * slice >= ((size_t)16 << 20))) { chunks = c; break; }
     const int m = n / chunks;
     push(v, FB_SHARD_STAGE, FB_STAGE_TRANSMITTANCE, 0, 0, 0, 0);
     push(v, FB_SHARD_STAGE, FB_STAGE_DIRECT_IRRADIANCE, 0, 0, 0, 0);
@@ -193,6 +193,7 @@ int make_plan(const FbParams& P, uint32_t order, int rank, int world, uint32_t f
     }
     int e0 = 0, e1 = P.irradiance_r_size;
     if (multi) irradiance_rows_of(P, rank, world, &e0, &e1);
+    bool result_gathered = false;
     for (uint32_t o = 2; o <= order; ++o) {
         for (int c = 0; c < chunks; ++c) {
             push(v, FB_SHARD_STAGE, FB_STAGE_SCATTERING_DENSITY, 0, o, a + c * m, a + (c + 1) * m);
@@ -210,7 +211,16 @@ int make_plan(const FbParams& P, uint32_t order, int rank, int world, uint32_t f
                     if (j >= q0 && j < q1) push(v, FB_SHARD_BCAST_ROWS, 0, FB_IMAGE_DELTA_IRRADIANCE, 0, j, j + 1, q);
                 }
         if (multi) push(v, FB_SHARD_JOIN, 0, 0, 0, 0, 0);
-        push(v, FB_SHARD_STAGE, FB_STAGE_MULTIPLE_SCATTERING, 0, 0, a, b);
+        if (multi && o == order && (flags & FB_SHARD_GATHER_RESULT) && chunks > 1) {
+            // the last pass finishes `scattering`: its sub-slabs leave for the other ranks behind the next sub-slab's kernel
+            for (int c = 0; c < chunks; ++c) {
+                push(v, FB_SHARD_STAGE, FB_STAGE_MULTIPLE_SCATTERING, 0, 0, a + c * m, a + (c + 1) * m);
+                push(v, FB_SHARD_ALLGATHER, 0, FB_IMAGE_SCATTERING, 0, c * m, (c + 1) * m);
+            }
+            result_gathered = true;
+        } else {
+            push(v, FB_SHARD_STAGE, FB_STAGE_MULTIPLE_SCATTERING, 0, 0, a, b);
+        }
         if (multi && o < order) {    // next order: density halo + irradiance rows read delta_multiple_scattering
             push(v, FB_SHARD_HALO, 0, FB_IMAGE_DELTA_MULTIPLE_SCATTERING, 0, 0, 0);
             push(v, FB_SHARD_JOIN, 0, 0, 0, 0, 0);
@@ -223,7 +233,7 @@ int make_plan(const FbParams& P, uint32_t order, int rank, int world, uint32_t f
                 irradiance_rows_of(P, q, world, &q0, &q1);
                 if (q1 > q0) push(v, FB_SHARD_BCAST_ROWS, 0, FB_IMAGE_IRRADIANCE, 0, q0, q1, q);
             }
-        if (flags & FB_SHARD_GATHER_RESULT) push(v, FB_SHARD_ALLGATHER, 0, FB_IMAGE_SCATTERING, 0, 0, n);
+        if ((flags & FB_SHARD_GATHER_RESULT) && !result_gathered) push(v, FB_SHARD_ALLGATHER, 0, FB_IMAGE_SCATTERING, 0, 0, n);
         push(v, FB_SHARD_JOIN, 0, 0, 0, 0, 0);
     }
     return FB_OK;

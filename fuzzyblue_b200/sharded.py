@@ -18,7 +18,7 @@ from typing import List, Tuple
 from . import api
 
 SHARD_STAGE, SHARD_ALLGATHER, SHARD_HALO, SHARD_BCAST_ROWS, SHARD_JOIN = range(5)
-GATHER_RESULT, NO_PIPELINE = 1, 2
+GATHER_RESULT, NO_PIPELINE, PIPELINE_ALWAYS = 1, 2, 4
 
 S3 = (api.IMAGE_SCATTERING, api.IMAGE_DELTA_RAYLEIGH, api.IMAGE_DELTA_MIE, api.IMAGE_SCATTERING_DENSITY,
       api.IMAGE_DELTA_MULTIPLE_SCATTERING)

@@ -333,6 +333,7 @@ typedef struct FbShardStep {
 } FbShardStep;
 #define FB_SHARD_GATHER_RESULT 1u /* finish with an all-gather of `scattering`: every rank ends with the whole table */
 #define FB_SHARD_NO_PIPELINE 2u   /* exchange whole slabs (one ncclAllGather) instead of sub-slabs behind the kernels */
+#define FB_SHARD_PIPELINE_ALWAYS 4u /* sub-slab exchanges even for tables whose sub-slabs are below 16 MiB (tests) */
 /* steps = NULL: only *count is written.  Transmittance and irradiance always end complete on every rank. */
 FB_API int fb_sharded_plan(const FbParams* p, uint32_t order, int rank, int world, uint32_t flags, FbShardStep* steps,
                            uint32_t capacity, uint32_t* count);

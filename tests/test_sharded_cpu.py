@@ -158,10 +158,12 @@ def test_plan_rejects_uneven_slabs():
         sharded.plan(fb.Parameters(), 2, 2)
 
 
-@pytest.mark.parametrize("order", [3, 4])
-def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order):
-    world, port = 2, 29500 + (os.getpid() % 2000) + order
-    mp.spawn(_worker, args=(world, port, order, str(tmp_path), sharded.GATHER_RESULT), nprocs=world, join=True)
+@pytest.mark.parametrize("order,pipelined", [(3, False), (4, False), (3, True)])
+def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order, pipelined):
+    """pipelined: sub-slab exchanges forced (2 sub-slabs per 2-level slab), the form the 2 GiB tables use."""
+    world, port = 2, 29500 + (os.getpid() % 2000) + order + (7 if pipelined else 0)
+    flags = sharded.GATHER_RESULT | (sharded.PIPELINE_ALWAYS if pipelined else 0)
+    mp.spawn(_worker, args=(world, port, order, str(tmp_path), flags), nprocs=world, join=True)
     ref = O.precompute(O.Params(order=order, **DIMS), O.F32)
     rows = 0
     for rank in range(world):
@@ -172,7 +174,8 @@ def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order):
         rows += int(got["rows"])
         # 2 single-scattering halos; per order: the density all-gather, (before the next order) the two ground rows of
         # delta_irradiance and the halo of delta_multiple_scattering; finally the irradiance rows of both ranks + the table
-        assert int(got["exchanges"]) == 2 + (order - 1) + (order - 2) * 3 + world + 1
+        chunks = 2 if pipelined else 1      # density per order in `chunks` pieces; the result in `chunks` pieces
+        assert int(got["exchanges"]) == 2 + chunks * (order - 1) + (order - 2) * 3 + world + chunks
     assert rows == (order - 1) * DIMS["irradiance_r_size"]          # every irradiance row evaluated exactly once per order
     # each rank's own slab of the last delta_multiple_scattering is current; of the peer's slab only the halo slice was
     # ever received, and that one order earlier (the last order's temporaries are not exchanged: nothing reads them)

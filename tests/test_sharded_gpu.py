@@ -72,7 +72,7 @@ def _worker(rank, world, port, out_dir, flags, kernels):
 
 
 @pytest.mark.parametrize("kernels", [0, 1], ids=["fast", "reference"])
-@pytest.mark.parametrize("flags", [1, 1 | 2], ids=["pipelined", "whole-slab"])
+@pytest.mark.parametrize("flags", [1 | 4, 1 | 2], ids=["pipelined", "whole-slab"])
 def test_two_gpu_sharded_build_is_bit_identical(tmp_path, flags, kernels):
     import torch
     import torch.multiprocessing as mp
