@@ -12,6 +12,7 @@
 #include "fb_kernels.h"
 
 #include <type_traits>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <algorithm>
@@ -1274,12 +1275,22 @@ static cudaError_t multiple_launch(const LaunchCtx& c, int nt, int CH, size_t sm
 // what the row-shared multiple-scattering kernel covers: a (nu, mu_s) row of at most 8192 texels whose staging slab fits
 // in shared memory (W = 8192: 17 KiB of node records + 128 KiB of slab).  Wider rows run the transcription (reported
 // through fb_params_slow_stages / fb_pending_slow_stages).
+// nodes staged per pass.  Rows of up to 1024 texels: a slab of <= 48 KiB, so that four CTAs share an SM.  Wider rows
+// run one 1024-thread CTA per SM anyway: their slab takes what the SM has (up to 3 nodes in <= 196 KiB), which cuts the
+// stage / consume barrier pairs of a row from 51 to 17 (FUZZYBLUE_B200_MS_WIDE_CH overrides, for measurements).
+static int multiple_chunk(int W) {
+    int CH = 3072 / W;
+    if (W > 1024) {
+        static const int forced = [] { const char* e = std::getenv("FUZZYBLUE_B200_MS_WIDE_CH"); return e ? std::atoi(e) : 0; }();
+        const int fit = (int)((196 * 1024) / ((size_t)W * sizeof(float4)));
+        CH = std::max(CH, std::min(forced > 0 ? forced : 3, fit));
+    }
+    return CH < 1 ? 1 : (CH > 17 ? 17 : CH);
+}
 bool multiple_is_fast(const FbParams& P) {
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     if (W > 8192 || P.scattering_mu_s_size < 2) return false;
-    int CH = 3072 / W;
-    CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
-    return sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4) <= 200 * 1024;
+    return sizeof(MultiNode) * NS + (size_t)multiple_chunk(W) * W * sizeof(float4) <= 200 * 1024;
 }
 
 cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
@@ -1288,8 +1299,7 @@ cudaError_t multiple_scattering(const LaunchCtx& c, int r0, int r1) {
     // default dims: 256 threads, 1 texel each; larger rows: up to 1024 threads x {1, 2, 4, 8} texels
     const int nt = W <= 1024 ? ((W + 31) / 32) * 32 : 1024;
     const int tpt = (W + nt - 1) / nt;
-    int CH = 3072 / W;                            // nodes staged per pass: slab = CH * W * 16 B <= 48 KiB (64 KiB for W = 4096)
-    CH = CH < 1 ? 1 : (CH > 17 ? 17 : CH);
+    const int CH = multiple_chunk(W);             // nodes staged per pass
     const size_t smem = sizeof(MultiNode) * NS + (size_t)CH * W * sizeof(float4);
     if (nt <= 256) return multiple_launch<1, 256>(c, nt, CH, smem, r0, r1);
     if (tpt == 1) return multiple_launch<1, 1024>(c, nt, CH, smem, r0, r1);
