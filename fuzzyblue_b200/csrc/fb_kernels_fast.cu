@@ -147,7 +147,7 @@ template <bool ORDER2>
 __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, Tex2 T,
                                                       Tex3 A0, Tex3 A1, DensityDims dd, float* __restrict__ tab,
                                                       float* __restrict__ hit, const float4* __restrict__ dE_row0,
-                                                      float2* __restrict__ grow, int r0) {
+                                                      float2* __restrict__ grow, int r0, int sw32) {
     constexpr int ENT = DensityCfg<ORDER2>::ENT, TT = DensityCfg<ORDER2>::T;
     const int l = blockIdx.y, z = r0 + blockIdx.z;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,9 +209,12 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
         o4[2] = make_float4(my.x, my.y, mz.x, mz.y);
     } else {
         float2* o2 = reinterpret_cast<float2*>(o);
-        o2[0] = seg(s0.x, s1.x);
-        o2[1] = seg(s0.y, s1.y);
-        o2[2] = seg(s0.z, s1.z);
+        // wide tables (nu > 16): entries 16..31, 48..63, ... as (slope, intercept) -- the bank swizzle tab3<true> reads
+        const bool swp = sw32 && (k & 16);
+        auto put = [swp](float2 v) { return swp ? make_float2(v.y, v.x) : v; };
+        o2[0] = put(seg(s0.x, s1.x));
+        o2[1] = put(seg(s0.y, s1.y));
+        o2[2] = put(seg(s0.z, s1.z));
     }
 }
 
@@ -230,6 +233,25 @@ template <int OFF> __device__ __forceinline__ float lds32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
     return v;
 }
+// One (intercept, slope) entry of the order >= 3 table: three 64-bit loads -- or, for tables of more than 16 nu knots
+// (SW32), six 32-bit loads from a bank-swizzled entry.  With 64-bit accesses a wavefront serves 16 lanes over 16 bank
+// pairs, and entries k and k + 16 of a row (24-byte stride) share a pair: at nu = 32 the phi samples of a warp reach
+// across more than 16 segments and 23 % of the wavefronts of the high-resolution launch were replays
+// (l1tex__data_bank_conflicts_pipe_lsu_mem_shared 1.2e9 of 5.3e9; 1 % at nu = 8).  k_density_prep therefore stores the
+// pairs of entries 16..31 (48..63, ...) as (slope, intercept): read as 32-bit words, entry k + 16 lands on the odd bank
+// of the pair entry k uses, and any set of entries 0..31 is conflict-free.  `sw` = 4 for a swapped entry, else 0.
+template <bool SW32, int OFF>
+__device__ __forceinline__ void tab3(uint32_t addr, uint32_t sw, float2& cr, float2& cg, float2& cb) {
+    if (!SW32) {
+        cr = lds64<OFF>(addr); cg = lds64<OFF + 8>(addr); cb = lds64<OFF + 16>(addr);
+    } else {
+        const uint32_t aI = addr + sw, aS = aI ^ 4u;        // addr is 8-byte aligned
+        cr.x = lds32<OFF>(aI); cg.x = lds32<OFF + 8>(aI); cb.x = lds32<OFF + 16>(aI);
+        cr.y = lds32<OFF>(aS); cg.y = lds32<OFF + 8>(aS); cb.y = lds32<OFF + 16>(aS);
+    }
+}
+__device__ __forceinline__ uint32_t tab_swap(float tm) { return (__float_as_uint(tm) >> 2) & 4u; }   // bit 4 of floor(tcx)
+
 __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; callers guarantee a normal, positive x
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -238,8 +260,8 @@ __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; caller
 
 // One sample of the integrand for the paired body's slow branch (a table knot between two mirror samples): the look-up
 // of FB_DENSITY_STEP as a function.  TOFF / GOFF are the immediate offsets of the theta row and of the ground rows.
-template <bool ORDER2, int TOFF, int GOFF>
-__device__ __forceinline__ void density_tap(uint32_t addr, float f, float nu1, float kR, float kMR, float g2p1, float m2g, bool gnd,
+template <bool ORDER2, bool SW32, int TOFF, int GOFF>
+__device__ __forceinline__ void density_tap(uint32_t addr, uint32_t sw, float f, float nu1, float kR, float kMR, float g2p1, float m2g, bool gnd,
                                             uint32_t ea, float te, float& Lr, float& Lg, float& Lb) {
     if (ORDER2) {
         const float4 t0 = lds128<TOFF>(addr), t1 = lds128<TOFF + 16>(addr), t2 = lds128<TOFF + 32>(addr);
@@ -250,7 +272,8 @@ __device__ __forceinline__ void density_tap(uint32_t addr, float f, float nu1, f
         Lg = fmaf(fmaf(f, t2.y, t2.x), pm, fmaf(f, t0.w, t0.z) * pr);
         Lb = fmaf(fmaf(f, t2.w, t2.z), pm, fmaf(f, t1.y, t1.x) * pr);
     } else {
-        const float2 cr = lds64<TOFF>(addr), cg = lds64<TOFF + 8>(addr), cb = lds64<TOFF + 16>(addr);
+        float2 cr, cg, cb;
+        tab3<SW32, TOFF>(addr, sw, cr, cg, cb);
         Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);
     }
     if (gnd) {
@@ -267,7 +290,7 @@ constexpr int GN_MAXR = 64;
 struct GroundNormals { float2 n[GN_MAXR][DL / 2]; };
 
 
-template <bool ORDER2>
+template <bool ORDER2, bool SW32>
 __global__ void __launch_bounds__(256, 2)
 k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig tg, DensityDims dd, const float* __restrict__ tabG,
                const float* __restrict__ hitG, const float2* __restrict__ growG, uint2* __restrict__ out, int r0,
@@ -489,8 +512,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                 Lg = fmaf(fmaf(f, t2.y, t2.x), pm, fmaf(f, t0.w, t0.z) * pr);                                           \
                 Lb = fmaf(fmaf(f, t2.w, t2.z), pm, fmaf(f, t1.y, t1.x) * pr);                                           \
             } else {                                                                                                    \
-                const float2 cr = lds64<(l) * L_STRIDE>(addr), cg = lds64<(l) * L_STRIDE + 8>(addr),                    \
-                             cb = lds64<(l) * L_STRIDE + 16>(addr);                                                     \
+                float2 cr, cg, cb;                                                                                      \
+                tab3<SW32, (l) * L_STRIDE>(addr, tab_swap(tm), cr, cg, cb);                                             \
                 Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);                           \
             }                                                                                                           \
             if (L0 >= 0 ? (l) >= L0 : ((l) >= DL / 2 && (gmask & (1u << (l))) != 0)) {  /* CTA-uniform */              \
@@ -590,8 +613,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                 Lb = fmaf(fmaf(fa, t2.w, t2.z), pma, fmaf(fa, t1.y, t1.x) * pra) +                                      \
                      fmaf(fmaf(fb, t2.w, t2.z), pmb, fmaf(fb, t1.y, t1.x) * prb);                                       \
             } else {                          /* half sums: the texel's total is doubled after the loop */              \
-                const float2 cr = lds64<(l) * L_STRIDE>(addr), cg = lds64<(l) * L_STRIDE + 8>(addr),                    \
-                             cb = lds64<(l) * L_STRIDE + 16>(addr);                                                     \
+                float2 cr, cg, cb;                                                                                      \
+                tab3<SW32, (l) * L_STRIDE>(addr, tab_swap(ta), cr, cg, cb);                                             \
                 Lr = fmaf(fm, cr.y, cr.x); Lg = fmaf(fm, cg.y, cg.x); Lb = fmaf(fm, cb.y, cb.x);                        \
             }                                                                                                           \
             if (gnd) {                                                                                                  \
@@ -643,11 +666,12 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                         fa = fmaf(qd, st, fm); fb = fmaf(qdn, st, fm);
                     }
                     const uint32_t lrow = row_t + (uint32_t)(l * L_STRIDE);
-                    const uint32_t addra = lrow + __float_as_uint(__fadd_rd(fa, MAGIC)) * (uint32_t)ENT_B;
-                    const uint32_t addrb = lrow + __float_as_uint(__fadd_rd(fb, MAGIC)) * (uint32_t)ENT_B;
+                    const float tma = __fadd_rd(fa, MAGIC), tmb = __fadd_rd(fb, MAGIC);
+                    const uint32_t addra = lrow + __float_as_uint(tma) * (uint32_t)ENT_B;
+                    const uint32_t addrb = lrow + __float_as_uint(tmb) * (uint32_t)ENT_B;
                     float r1, g1, b1, r2, g2, b2;
-                    density_tap<ORDER2, 0, GR_OFF>(addrb, fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r1, g1, b1);
-                    density_tap<ORDER2, 0, GR_OFF>(addra, fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r2, g2, b2);
+                    density_tap<ORDER2, SW32, 0, GR_OFF>(addrb, tab_swap(tmb), fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r1, g1, b1);
+                    density_tap<ORDER2, SW32, 0, GR_OFF>(addra, tab_swap(tma), fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r2, g2, b2);
                     dr = hs * (r1 - r2); dg = hs * (g1 - g2); db = hs * (b1 - b2);
                 }
                 if (straddle & (0x10000u << l)) {                                  // only ever set for l >= DL / 2
@@ -687,7 +711,7 @@ template <bool ORDER2> static size_t density_smem(const FbParams& P) {
     return (size_t)DL * C::T * C::ENT * 4 + C::T * 16 + 128 + (wt > gr ? wt : gr);
 }
 
-template <bool ORDER2>
+template <bool ORDER2, bool SW32>
 static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, int r1, cudaEvent_t after_prep) {
     typedef DensityCfg<ORDER2> C;
     const FbParams& P = c.P;
@@ -698,12 +722,12 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
     float* hit = tab + density_tab_floats(P) + density_grow_floats(P);
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
     dim3 gp((W + 255) / 256, DL, r1 - r0);
-    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, hit, c.img.delta_irradiance, grow, r0);
+    k_density_prep<ORDER2><<<gp, 256, 0, c.stream>>>(P, c.trig, texT(c), A0, A1, d, tab, hit, c.img.delta_irradiance, grow, r0, SW32 ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // from here on nothing reads delta_irradiance: indirect_irradiance may run concurrently with the main kernel
     if (after_prep && (e = cudaEventRecord(after_prep, c.stream)) != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_density_main<ORDER2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k_density_main<ORDER2, SW32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // ground normals (scattering_density.comp:81-87) per (r, downward theta row); the look-up coordinate the kernel forms
     // is te = (q n_x + mu_s n_z + 1) e_c with e_c = (nE - 1) / 2, and at order >= 3 its q, mu_s carry hn = (nu - 1) / 2
@@ -724,7 +748,7 @@ static cudaError_t density_launch(const LaunchCtx& c, Tex3 A0, Tex3 A1, int r0, 
             }
         }
         dim3 gm(d.tiles, P.scattering_mu_size, nz_);
-        k_density_main<ORDER2><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, hit, grow, c.img.scattering_density, zc,
+        k_density_main<ORDER2, SW32><<<gm, C::NWARPS * 32, smem, c.stream>>>(P, c.trig, d, tab, hit, grow, c.img.scattering_density, zc,
                                                                       0x4B000000u * (uint32_t)(C::ENT * 4), 0x4B000000u * 24u, gn
                                                                       );
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -738,8 +762,11 @@ cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cu
         if (e == cudaSuccess && after_prep) e = cudaEventRecord(after_prep, c.stream);
         return e;
     }
-    if (order == 2) return density_launch<true>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1, after_prep);
-    return density_launch<false>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1, after_prep);
+    if (order == 2) return density_launch<true, false>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1, after_prep);
+    // more than 16 nu knots: bank-swizzled table entries read with 32-bit loads (tab3)
+    if (c.P.scattering_nu_size > 16)
+        return density_launch<false, true>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1, after_prep);
+    return density_launch<false, false>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1, after_prep);
 }
 
 // ---------------------------------------------------------------------------------------------

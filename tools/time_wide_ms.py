@@ -24,9 +24,11 @@ with torch.cuda.stream(s):
             best = min(best, e0.elapsed_time(e1))
         out[name] = best
 s.synchronize()
-ptr, nbytes = p.image(api.IMAGE_DELTA_MULTIPLE_SCATTERING)
-class _Raw:
-    __cuda_array_interface__ = {"shape": (nbytes // 8 // 8,), "typestr": "<u8", "data": (ptr, False), "version": 2}
-t = torch.as_tensor(_Raw(), device="cuda")      # first 1/8 of the table = the slab
-h = hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()[:16]
-print("MS_WIDE_CH=%s: " % os.environ.get("FUZZYBLUE_B200_MS_WIDE_CH", "default") + ", ".join(f"{k} {v:.2f} ms" for k, v in out.items()) + f" | dMS slab hash {h}")
+def slab_hash(image):
+    ptr, nbytes = p.image(image)
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (nbytes // 8 // 8,), "typestr": "<u8", "data": (ptr, False), "version": 2}
+    t = torch.as_tensor(_Raw(), device="cuda")      # first 1/8 of the table = the slab
+    return hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest()[:16]
+print("MS_WIDE_CH=%s: " % os.environ.get("FUZZYBLUE_B200_MS_WIDE_CH", "default") + ", ".join(f"{k} {v:.2f} ms" for k, v in out.items())
+      + f" | dMS slab hash {slab_hash(api.IMAGE_DELTA_MULTIPLE_SCATTERING)} density(order 3) slab hash {slab_hash(api.IMAGE_SCATTERING_DENSITY)}")
