@@ -203,10 +203,11 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
         const V4<F> m1 = last ? m0 : sample<F>(A1, ux1, uvwz[2], uvwz[3]);
         const float2 rx = seg(s0.x, s1.x), ry = seg(s0.y, s1.y), rz = seg(s0.z, s1.z);
         const float2 mx = seg(m0.x, m1.x), my = seg(m0.y, m1.y), mz = seg(m0.z, m1.z);
-        float4* o4 = reinterpret_cast<float4*>(o);
-        o4[0] = make_float4(rx.x, rx.y, ry.x, ry.y);
-        o4[1] = make_float4(rz.x, rz.y, mx.x, mx.y);
-        o4[2] = make_float4(my.x, my.y, mz.x, mz.y);
+        // wide tables (nu > 16): the words of each group of four at position j ^ s, s = (k >> 3) & 3 (tab12<true> reads them so)
+        const int sx = sw32 ? (k >> 3) & 3 : 0;
+        const float w12[12] = {rx.x, rx.y, ry.x, ry.y, rz.x, rz.y, mx.x, mx.y, my.x, my.y, mz.x, mz.y};
+#pragma unroll
+        for (int j = 0; j < 12; ++j) o[(j & ~3) | ((j & 3) ^ sx)] = w12[j];
     } else {
         float2* o2 = reinterpret_cast<float2*>(o);
         // wide tables (nu > 16): entries 16..31, 48..63, ... as (slope, intercept) -- the bank swizzle tab3<true> reads
@@ -251,6 +252,22 @@ __device__ __forceinline__ void tab3(uint32_t addr, uint32_t sw, float2& cr, flo
     }
 }
 __device__ __forceinline__ uint32_t tab_swap(float tm) { return (__float_as_uint(tm) >> 2) & 4u; }   // bit 4 of floor(tcx)
+// The order-2 entry (twelve words, 48-byte stride): three 128-bit loads -- or, SW32, twelve 32-bit loads from an entry
+// whose words are permuted inside each aligned group of four by XOR with s = (k >> 3) & 3 (k_density_prep writes them
+// so): entries k, k + 8, k + 16, k + 24 of a row start on the same bank, and the permutation spreads the same logical
+// word of the four over the four banks of its group, so any set of entries 0..31 is conflict-free.
+template <bool SW32, int OFF>
+__device__ __forceinline__ void tab12(uint32_t addr, float tm, float4& t0, float4& t1, float4& t2) {
+    if (!SW32) {
+        t0 = lds128<OFF>(addr); t1 = lds128<OFF + 16>(addr); t2 = lds128<OFF + 32>(addr);
+    } else {
+        const uint32_t a0 = addr + ((__float_as_uint(tm) >> 1) & 12u);      // addr is 16-byte aligned: word j of a group sits at (4 j) ^ (4 s)
+        const uint32_t a1 = a0 ^ 4u, a2 = a0 ^ 8u, a3 = a0 ^ 12u;
+        t0.x = lds32<OFF>(a0); t0.y = lds32<OFF>(a1); t0.z = lds32<OFF>(a2); t0.w = lds32<OFF>(a3);
+        t1.x = lds32<OFF + 16>(a0); t1.y = lds32<OFF + 16>(a1); t1.z = lds32<OFF + 16>(a2); t1.w = lds32<OFF + 16>(a3);
+        t2.x = lds32<OFF + 32>(a0); t2.y = lds32<OFF + 32>(a1); t2.z = lds32<OFF + 32>(a2); t2.w = lds32<OFF + 32>(a3);
+    }
+}
 
 __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; callers guarantee a normal, positive x
     float y;
@@ -261,10 +278,11 @@ __device__ __forceinline__ float rsqrt_fast(float x) {   // one MUFU.RSQ; caller
 // One sample of the integrand for the paired body's slow branch (a table knot between two mirror samples): the look-up
 // of FB_DENSITY_STEP as a function.  TOFF / GOFF are the immediate offsets of the theta row and of the ground rows.
 template <bool ORDER2, bool SW32, int TOFF, int GOFF>
-__device__ __forceinline__ void density_tap(uint32_t addr, uint32_t sw, float f, float nu1, float kR, float kMR, float g2p1, float m2g, bool gnd,
+__device__ __forceinline__ void density_tap(uint32_t addr, uint32_t sw, float tmf, float f, float nu1, float kR, float kMR, float g2p1, float m2g, bool gnd,
                                             uint32_t ea, float te, float& Lr, float& Lg, float& Lb) {
     if (ORDER2) {
-        const float4 t0 = lds128<TOFF>(addr), t1 = lds128<TOFF + 16>(addr), t2 = lds128<TOFF + 32>(addr);
+        float4 t0, t1, t2;
+        tab12<SW32, TOFF>(addr, tmf, t0, t1, t2);
         const float pr = fmaf(nu1 * kR, nu1, kR);
         const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));
         const float pm = pr * kMR * (rs * rs * rs);
@@ -503,8 +521,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             const uint32_t addr = row_t + __float_as_uint(tm) * (uint32_t)ENT_B;                                        \
             float Lr, Lg, Lb;                                                                                           \
             if (ORDER2) {                                                                                               \
-                const float4 t0 = lds128<(l) * L_STRIDE>(addr), t1 = lds128<(l) * L_STRIDE + 16>(addr),                 \
-                             t2 = lds128<(l) * L_STRIDE + 32>(addr);                                                    \
+                float4 t0, t1, t2;                                                                                      \
+                tab12<SW32, (l) * L_STRIDE>(addr, tm, t0, t1, t2);                                                      \
                 const float pr = fmaf(nu1 * kR, nu1, kR);                         /* util.h:26-29 */                    \
                 const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));                                                      \
                 const float pm = pr * kMR * (rs * rs * rs);                       /* util.h:31-34: x^-1.5 = rsqrt^3 */  \
@@ -601,8 +619,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             const uint32_t addr = row_t + __float_as_uint(ta) * (uint32_t)ENT_B;                                        \
             float Lr, Lg, Lb;                                                                                           \
             if (ORDER2) {                                                                                               \
-                const float4 t0 = lds128<(l) * L_STRIDE>(addr), t1 = lds128<(l) * L_STRIDE + 16>(addr),                 \
-                             t2 = lds128<(l) * L_STRIDE + 32>(addr);                                                    \
+                float4 t0, t1, t2;                                                                                      \
+                tab12<SW32, (l) * L_STRIDE>(addr, ta, t0, t1, t2);                                                      \
                 const float pra = fmaf(nu1a * kR, nu1a, kR), prb = fmaf(nu1b * kR, nu1b, kR);                           \
                 const float rsa = rsqrt_fast(fmaf(m2g, nu1a, g2p1)), rsb = rsqrt_fast(fmaf(m2g, nu1b, g2p1));           \
                 const float pma = pra * kMR * (rsa * rsa * rsa), pmb = prb * kMR * (rsb * rsb * rsb);                   \
@@ -670,8 +688,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                     const uint32_t addra = lrow + __float_as_uint(tma) * (uint32_t)ENT_B;
                     const uint32_t addrb = lrow + __float_as_uint(tmb) * (uint32_t)ENT_B;
                     float r1, g1, b1, r2, g2, b2;
-                    density_tap<ORDER2, SW32, 0, GR_OFF>(addrb, tab_swap(tmb), fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r1, g1, b1);
-                    density_tap<ORDER2, SW32, 0, GR_OFF>(addra, tab_swap(tma), fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r2, g2, b2);
+                    density_tap<ORDER2, SW32, 0, GR_OFF>(addrb, tab_swap(tmb), tmb, fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r1, g1, b1);
+                    density_tap<ORDER2, SW32, 0, GR_OFF>(addra, tab_swap(tma), tma, fb, nu1b, kR, kMR, g2p1, m2g, false, 0u, 0.f, r2, g2, b2);
                     dr = hs * (r1 - r2); dg = hs * (g1 - g2); db = hs * (b1 - b2);
                 }
                 if (straddle & (0x10000u << l)) {                                  // only ever set for l >= DL / 2
@@ -762,8 +780,10 @@ cudaError_t scattering_density(const LaunchCtx& c, int order, int r0, int r1, cu
         if (e == cudaSuccess && after_prep) e = cudaEventRecord(after_prep, c.stream);
         return e;
     }
+    // more than 16 nu knots: bank-swizzled table entries read with 32-bit loads (tab3 / tab12)
+    if (order == 2 && c.P.scattering_nu_size > 16)
+        return density_launch<true, true>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1, after_prep);
     if (order == 2) return density_launch<true, false>(c, texS(c, c.img.delta_rayleigh), texS(c, c.img.delta_mie), r0, r1, after_prep);
-    // more than 16 nu knots: bank-swizzled table entries read with 32-bit loads (tab3)
     if (c.P.scattering_nu_size > 16)
         return density_launch<false, true>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1, after_prep);
     return density_launch<false, false>(c, texS(c, c.img.delta_multiple_scattering), texS(c, c.img.delta_multiple_scattering), r0, r1, after_prep);
