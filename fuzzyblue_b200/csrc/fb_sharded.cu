@@ -178,8 +178,9 @@ int make_plan(const FbParams& P, uint32_t order, int rank, int world, uint32_t f
     // when a sub-slab is a real transfer (>= 16 MiB), small tables go in one piece
     const size_t slice = image_bytes(P, FB_IMAGE_SCATTERING) / R;
     int chunks = 1;
+    static const int max_chunks = [] { const char* e = std::getenv("FUZZYBLUE_B200_SHARD_CHUNKS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 4; }();
     if (multi && !(flags & FB_SHARD_NO_PIPELINE))
-        for (int c = std::min(4, n); c >= 1; --c)
+        for (int c = std::min(max_chunks, n); c >= 1; --c)
             if (n % c == 0 && ((flags & FB_SHARD_PIPELINE_ALWAYS) || (size_t)(n / c) * slice >= ((size_t)16 << 20))) { chunks = c; break; }
     const int m = n / chunks;
     push(v, FB_SHARD_STAGE, FB_STAGE_TRANSMITTANCE, 0, 0, 0, 0);
