@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
                 const float4 v0 = __ldg(dE_row0 + i), v1 = __ldg(dE_row0 + min(i + 1, nE - 1));
                 // (intercept, slope) of the segment [i, i + 1): value(te) = intercept + te * slope, no fractional part needed
                 const float dx_ = gx * (v1.x - v0.x), dy_ = gy * (v1.y - v0.y), dz_ = gz * (v1.z - v0.z), fi = (float)i;
-                o[i * 3] = make_float2(fmaf(-fi, dx_, gx * v0.x), dx_);
-                o[i * 3 + 1] = make_float2(fmaf(-fi, dy_, gy * v0.y), dy_);
-                o[i * 3 + 2] = make_float2(fmaf(-fi, dz_, gz * v0.z), dz_);
+                o[i * 3] = make_float2(fmaf(-fi, dx_, gx * v0.x), fmaf(-fi, dy_, gy * v0.y));   // (red, green) intercepts
+                o[i * 3 + 1] = make_float2(dx_, dy_);                                            // (red, green) slopes
+                o[i * 3 + 2] = make_float2(fmaf(-fi, dz_, gz * v0.z), dz_);                      // blue (intercept, slope)
             }
         }
     }
@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
         const float2 mx = seg(m0.x, m1.x), my = seg(m0.y, m1.y), mz = seg(m0.z, m1.z);
         // wide tables (nu > 16): the words of each group of four at position j ^ s, s = (k >> 3) & 3 (tab12<true> reads them so)
         const int sx = sw32 ? (k >> 3) & 3 : 0;
-        const float w12[12] = {rx.x, rx.y, ry.x, ry.y, rz.x, rz.y, mx.x, mx.y, my.x, my.y, mz.x, mz.y};
+        // words: Rayleigh (red, green) intercepts, slopes | Mie (red, green) intercepts, slopes | blue: Rayleigh, Mie pairs --
+        // the red and green channels of a sample are evaluated by one packed instruction (FFMA2, see P2 below)
+        const float w12[12] = {rx.x, ry.x, rx.y, ry.y, mx.x, my.x, mx.y, my.y, rz.x, rz.y, mz.x, mz.y};
 #pragma unroll
         for (int j = 0; j < 12; ++j) o[(j & ~3) | ((j & 3) ^ sx)] = w12[j];
     } else {
@@ -213,9 +215,10 @@ __global__ void __launch_bounds__(256) k_density_prep(const __grid_constant__ Fb
         // wide tables (nu > 16): entries 16..31, 48..63, ... as (slope, intercept) -- the bank swizzle tab3<true> reads
         const bool swp = sw32 && (k & 16);
         auto put = [swp](float2 v) { return swp ? make_float2(v.y, v.x) : v; };
-        o2[0] = put(seg(s0.x, s1.x));
-        o2[1] = put(seg(s0.y, s1.y));
-        o2[2] = put(seg(s0.z, s1.z));
+        const float2 sr = seg(s0.x, s1.x), sg = seg(s0.y, s1.y);
+        o2[0] = put(make_float2(sr.x, sg.x));              // (red, green) intercepts
+        o2[1] = put(make_float2(sr.y, sg.y));              // (red, green) slopes
+        o2[2] = put(seg(s0.z, s1.z));                      // blue (intercept, slope)
     }
 }
 
@@ -228,6 +231,26 @@ template <int OFF> __device__ __forceinline__ float2 lds64(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(addr), "n"(OFF));
     return v;
+}
+// Packed fp32 pairs (sm_100: FFMA2, FMUL2, FADD2).  Each half is the scalar IEEE operation, so results keep their bits;
+// one warp-instruction produces the red and the green channel (tools/ffma2_bench.cu: an FFMA2 holds the FMA pipe for two
+// cycles like two FFMA but takes ONE issue slot).  add2 / mul2 are only ever applied to results of fused multiply-adds
+// or feed one as the addend, where ptxas has nothing to contract (it does contract mul.rn.f32x2 + add.rn.f32x2).
+struct P2 { unsigned long long v; };
+__device__ __forceinline__ P2 pk(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(P2 p, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p.v)); }
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) { P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ P2 sub2(P2 a, P2 b) { P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ P2 bc(float f) { return pk(f, f); }
+template <int OFF> __device__ __forceinline__ P2 lds64p(uint32_t addr) {
+    P2 v;
+    asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(v.v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ void lds128p(uint32_t addr, P2& lo, P2& hi) {
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2+%3];" : "=l"(lo.v), "=l"(hi.v) : "r"(addr), "n"(OFF));
 }
 template <int OFF> __device__ __forceinline__ float lds32(uint32_t addr) {
     float v;
@@ -242,13 +265,13 @@ template <int OFF> __device__ __forceinline__ float lds32(uint32_t addr) {
 // pairs of entries 16..31 (48..63, ...) as (slope, intercept): read as 32-bit words, entry k + 16 lands on the odd bank
 // of the pair entry k uses, and any set of entries 0..31 is conflict-free.  `sw` = 4 for a swapped entry, else 0.
 template <bool SW32, int OFF>
-__device__ __forceinline__ void tab3(uint32_t addr, uint32_t sw, float2& cr, float2& cg, float2& cb) {
+__device__ __forceinline__ void tab3(uint32_t addr, uint32_t sw, P2& irg, P2& srg, float2& cb) {   // (r, g) intercepts, slopes; blue pair
     if (!SW32) {
-        cr = lds64<OFF>(addr); cg = lds64<OFF + 8>(addr); cb = lds64<OFF + 16>(addr);
+        irg = lds64p<OFF>(addr); srg = lds64p<OFF + 8>(addr); cb = lds64<OFF + 16>(addr);
     } else {
         const uint32_t aI = addr + sw, aS = aI ^ 4u;        // addr is 8-byte aligned
-        cr.x = lds32<OFF>(aI); cg.x = lds32<OFF + 8>(aI); cb.x = lds32<OFF + 16>(aI);
-        cr.y = lds32<OFF>(aS); cg.y = lds32<OFF + 8>(aS); cb.y = lds32<OFF + 16>(aS);
+        irg = pk(lds32<OFF>(aI), lds32<OFF>(aS)); srg = pk(lds32<OFF + 8>(aI), lds32<OFF + 8>(aS));
+        cb.x = lds32<OFF + 16>(aI); cb.y = lds32<OFF + 16>(aS);
     }
 }
 __device__ __forceinline__ uint32_t tab_swap(float tm) { return (__float_as_uint(tm) >> 2) & 4u; }   // bit 4 of floor(tcx)
@@ -257,15 +280,15 @@ __device__ __forceinline__ uint32_t tab_swap(float tm) { return (__float_as_uint
 // so): entries k, k + 8, k + 16, k + 24 of a row start on the same bank, and the permutation spreads the same logical
 // word of the four over the four banks of its group, so any set of entries 0..31 is conflict-free.
 template <bool SW32, int OFF>
-__device__ __forceinline__ void tab12(uint32_t addr, float tm, float4& t0, float4& t1, float4& t2) {
+__device__ __forceinline__ void tab12(uint32_t addr, float tm, P2& Ri, P2& Rs, P2& Mi, P2& Ms, float4& tb) {
     if (!SW32) {
-        t0 = lds128<OFF>(addr); t1 = lds128<OFF + 16>(addr); t2 = lds128<OFF + 32>(addr);
+        lds128p<OFF>(addr, Ri, Rs); lds128p<OFF + 16>(addr, Mi, Ms); tb = lds128<OFF + 32>(addr);
     } else {
         const uint32_t a0 = addr + ((__float_as_uint(tm) >> 1) & 12u);      // addr is 16-byte aligned: word j of a group sits at (4 j) ^ (4 s)
         const uint32_t a1 = a0 ^ 4u, a2 = a0 ^ 8u, a3 = a0 ^ 12u;
-        t0.x = lds32<OFF>(a0); t0.y = lds32<OFF>(a1); t0.z = lds32<OFF>(a2); t0.w = lds32<OFF>(a3);
-        t1.x = lds32<OFF + 16>(a0); t1.y = lds32<OFF + 16>(a1); t1.z = lds32<OFF + 16>(a2); t1.w = lds32<OFF + 16>(a3);
-        t2.x = lds32<OFF + 32>(a0); t2.y = lds32<OFF + 32>(a1); t2.z = lds32<OFF + 32>(a2); t2.w = lds32<OFF + 32>(a3);
+        Ri = pk(lds32<OFF>(a0), lds32<OFF>(a1)); Rs = pk(lds32<OFF>(a2), lds32<OFF>(a3));
+        Mi = pk(lds32<OFF + 16>(a0), lds32<OFF + 16>(a1)); Ms = pk(lds32<OFF + 16>(a2), lds32<OFF + 16>(a3));
+        tb.x = lds32<OFF + 32>(a0); tb.y = lds32<OFF + 32>(a1); tb.z = lds32<OFF + 32>(a2); tb.w = lds32<OFF + 32>(a3);
     }
 }
 
@@ -281,22 +304,24 @@ template <bool ORDER2, bool SW32, int TOFF, int GOFF>
 __device__ __forceinline__ void density_tap(uint32_t addr, uint32_t sw, float tmf, float f, float nu1, float kR, float kMR, float g2p1, float m2g, bool gnd,
                                             uint32_t ea, float te, float& Lr, float& Lg, float& Lb) {
     if (ORDER2) {
-        float4 t0, t1, t2;
-        tab12<SW32, TOFF>(addr, tmf, t0, t1, t2);
+        P2 Ri, Rs, Mi, Ms; float4 tb;
+        tab12<SW32, TOFF>(addr, tmf, Ri, Rs, Mi, Ms, tb);
         const float pr = fmaf(nu1 * kR, nu1, kR);
         const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));
         const float pm = pr * kMR * (rs * rs * rs);
-        Lr = fmaf(fmaf(f, t1.w, t1.z), pm, fmaf(f, t0.y, t0.x) * pr);
-        Lg = fmaf(fmaf(f, t2.y, t2.x), pm, fmaf(f, t0.w, t0.z) * pr);
-        Lb = fmaf(fmaf(f, t2.w, t2.z), pm, fmaf(f, t1.y, t1.x) * pr);
+        upk(fma2(fma2(bc(f), Ms, Mi), bc(pm), mul2(fma2(bc(f), Rs, Ri), bc(pr))), Lr, Lg);
+        Lb = fmaf(fmaf(f, tb.w, tb.z), pm, fmaf(f, tb.y, tb.x) * pr);
     } else {
-        float2 cr, cg, cb;
-        tab3<SW32, TOFF>(addr, sw, cr, cg, cb);
-        Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);
+        P2 irg, srg; float2 cb;
+        tab3<SW32, TOFF>(addr, sw, irg, srg, cb);
+        upk(fma2(bc(f), srg, irg), Lr, Lg); Lb = fmaf(f, cb.y, cb.x);
     }
     if (gnd) {
-        const float2 er = lds64<GOFF>(ea), eg = lds64<GOFF + 8>(ea), eb = lds64<GOFF + 16>(ea);
-        Lr += fmaf(te, er.y, er.x); Lg += fmaf(te, eg.y, eg.x); Lb += fmaf(te, eb.y, eb.x);
+        const P2 ei = lds64p<GOFF>(ea), es = lds64p<GOFF + 8>(ea);
+        const float2 eb = lds64<GOFF + 16>(ea);
+        float gr, gg;
+        upk(fma2(bc(te), es, ei), gr, gg);
+        Lr += gr; Lg += gg; Lb += fmaf(te, eb.y, eb.x);
     }
 }
 
@@ -397,11 +422,12 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
     __syncthreads();
 
     // ---- per-lane constants: the weights of phi sample `lane` for the 16 theta rows (registers) ------------
-    float Wr[DL], Wg[DL], Wb[DL];
+    P2 Wrg[DL];                                                                // (red, green) as one packed operand
+    float Wb[DL];
 #pragma unroll
     for (int l = 0; l < DL; ++l) {
         const float4 w = WtS[l * 32 + lane];
-        Wr[l] = w.x; Wg[l] = w.y; Wb[l] = w.z;
+        Wrg[l] = pk(w.x, w.y); Wb[l] = w.z;
     }
     // ---- work list ------------------------------------------------------------------------------------------
     // Every nu knot outside [mu mu_s - s, mu mu_s + s] is clamped onto the same bound (scattering.h:133-136), so a
@@ -510,7 +536,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         }
         if (!ORDER2) { q *= hn; mus *= hn; }                                      // tcx = hn * nu1 + hn in two FFMAs
         const uint32_t row_t = tab_base + ((uint32_t)__float_as_int(geo.w) & 0x3fffu);
-        ar = 0.f; ag = 0.f; ab = 0.f;
+        P2 arg = pk(0.f, 0.f);
+        ab = 0.f;
 #define FB_DENSITY_STEP(l)                                                                                              \
         {                                                                                                               \
             float nu1, tcx;                                                       /* scattering.h:146, in [0, nu-1) */  \
@@ -519,20 +546,20 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             const float tm = __fadd_rd(tcx, MAGIC);                               /* floor(tcx) in the low mantissa */  \
             const float f = tcx;                                                  /* entries are (intercept, slope) */  \
             const uint32_t addr = row_t + __float_as_uint(tm) * (uint32_t)ENT_B;                                        \
-            float Lr, Lg, Lb;                                                                                           \
+            P2 Lrg; float Lb;                                                     /* (red, green) packed, blue */       \
             if (ORDER2) {                                                                                               \
-                float4 t0, t1, t2;                                                                                      \
-                tab12<SW32, (l) * L_STRIDE>(addr, tm, t0, t1, t2);                                                      \
+                P2 Ri, Rs, Mi, Ms; float4 tb;                                                                           \
+                tab12<SW32, (l) * L_STRIDE>(addr, tm, Ri, Rs, Mi, Ms, tb);                                              \
                 const float pr = fmaf(nu1 * kR, nu1, kR);                         /* util.h:26-29 */                    \
                 const float rs = rsqrt_fast(fmaf(m2g, nu1, g2p1));                                                      \
                 const float pm = pr * kMR * (rs * rs * rs);                       /* util.h:31-34: x^-1.5 = rsqrt^3 */  \
-                Lr = fmaf(fmaf(f, t1.w, t1.z), pm, fmaf(f, t0.y, t0.x) * pr);     /* scattering.h:172-173 */            \
-                Lg = fmaf(fmaf(f, t2.y, t2.x), pm, fmaf(f, t0.w, t0.z) * pr);                                           \
-                Lb = fmaf(fmaf(f, t2.w, t2.z), pm, fmaf(f, t1.y, t1.x) * pr);                                           \
+                const P2 f2 = bc(f);                                                                                    \
+                Lrg = fma2(fma2(f2, Ms, Mi), bc(pm), mul2(fma2(f2, Rs, Ri), bc(pr)));   /* scattering.h:172-173 */      \
+                Lb = fmaf(fmaf(f, tb.w, tb.z), pm, fmaf(f, tb.y, tb.x) * pr);                                           \
             } else {                                                                                                    \
-                float2 cr, cg, cb;                                                                                      \
-                tab3<SW32, (l) * L_STRIDE>(addr, tab_swap(tm), cr, cg, cb);                                             \
-                Lr = fmaf(f, cr.y, cr.x); Lg = fmaf(f, cg.y, cg.x); Lb = fmaf(f, cb.y, cb.x);                           \
+                P2 irg, srg; float2 cb;                                                                                 \
+                tab3<SW32, (l) * L_STRIDE>(addr, tab_swap(tm), irg, srg, cb);                                           \
+                Lrg = fma2(bc(f), srg, irg); Lb = fmaf(f, cb.y, cb.x);                                                  \
             }                                                                                                           \
             if (L0 >= 0 ? (l) >= L0 : ((l) >= DL / 2 && (gmask & (1u << (l))) != 0)) {  /* CTA-uniform */              \
                 const float2 N = GN.n[blockIdx.z][(l) - DL / 2];                  /* ground normal, uniform regs */     \
@@ -541,18 +568,19 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                 const float em = __fadd_rd(te, MAGIC);                                                                  \
                 const float fe = te;                                                                                    \
                 const uint32_t ea = erow_t + (uint32_t)((l) - DL / 2) * grow_b + __float_as_uint(em) * 24u;             \
-                const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);           \
-                Lr += fmaf(fe, er.y, er.x);                                       /* rows carry the ground factor */    \
-                Lg += fmaf(fe, eg.y, eg.x);                                                                             \
+                const P2 ei = lds64p<GR_OFF>(ea), es = lds64p<GR_OFF + 8>(ea);                                          \
+                const float2 eb = lds64<GR_OFF + 16>(ea);                                                               \
+                Lrg = add2(Lrg, fma2(bc(fe), es, ei));                            /* rows carry the ground factor */    \
                 Lb += fmaf(fe, eb.y, eb.x);                                                                             \
             }                                                                                                           \
-            ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);                               \
+            arg = fma2(Lrg, Wrg[l], arg); ab = fmaf(Lb, Wb[l], ab);                                                     \
         }
         FB_DENSITY_STEP(0) FB_DENSITY_STEP(1) FB_DENSITY_STEP(2) FB_DENSITY_STEP(3)
         FB_DENSITY_STEP(4) FB_DENSITY_STEP(5) FB_DENSITY_STEP(6) FB_DENSITY_STEP(7)
         FB_DENSITY_STEP(8) FB_DENSITY_STEP(9) FB_DENSITY_STEP(10) FB_DENSITY_STEP(11)
         FB_DENSITY_STEP(12) FB_DENSITY_STEP(13) FB_DENSITY_STEP(14) FB_DENSITY_STEP(15)
 #undef FB_DENSITY_STEP
+        upk(arg, ar, ag);
     };
     // Two texels per iteration: their partial sums meet in ONE butterfly -- the first exchange hands texel 0 to lanes 0-15
     // and texel 1 to lanes 16-31 (3 shuffles for both texels instead of 6), the remaining four steps run on half-warps.
@@ -600,7 +628,8 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         const float qm = qm0 * sc, qd = qd0 * sc, qdn = -qd;
         mus *= sc;
         const uint32_t row_t = tab_base + ((uint32_t)__float_as_int(geo.w) & 0x3fffu);
-        float ar = 0.f, ag = 0.f, ab = 0.f;
+        P2 arg = pk(0.f, 0.f);
+        float ab = 0.f;
         uint32_t straddle = 0;                                                   // bit l: table knot, bit 16 + l: ground-row knot
 #define FB_PAIR_STEP(l)                                                                                                 \
         {                                                                                                               \
@@ -617,23 +646,22 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
             const float ta = __fadd_rd(fa, MAGIC), tb = __fadd_rd(fb, MAGIC);                                           \
             if (ta != tb) straddle |= 1u << (l);                                  /* a nu knot between the two */       \
             const uint32_t addr = row_t + __float_as_uint(ta) * (uint32_t)ENT_B;                                        \
-            float Lr, Lg, Lb;                                                                                           \
+            P2 Lrg; float Lb;                                                                                           \
             if (ORDER2) {                                                                                               \
-                float4 t0, t1, t2;                                                                                      \
-                tab12<SW32, (l) * L_STRIDE>(addr, ta, t0, t1, t2);                                                      \
+                P2 Ri, Rs, Mi, Ms; float4 tb;                                                                           \
+                tab12<SW32, (l) * L_STRIDE>(addr, ta, Ri, Rs, Mi, Ms, tb);                                              \
                 const float pra = fmaf(nu1a * kR, nu1a, kR), prb = fmaf(nu1b * kR, nu1b, kR);                           \
                 const float rsa = rsqrt_fast(fmaf(m2g, nu1a, g2p1)), rsb = rsqrt_fast(fmaf(m2g, nu1b, g2p1));           \
                 const float pma = pra * kMR * (rsa * rsa * rsa), pmb = prb * kMR * (rsb * rsb * rsb);                   \
-                Lr = fmaf(fmaf(fa, t1.w, t1.z), pma, fmaf(fa, t0.y, t0.x) * pra) +                                      \
-                     fmaf(fmaf(fb, t1.w, t1.z), pmb, fmaf(fb, t0.y, t0.x) * prb);                                       \
-                Lg = fmaf(fmaf(fa, t2.y, t2.x), pma, fmaf(fa, t0.w, t0.z) * pra) +                                      \
-                     fmaf(fmaf(fb, t2.y, t2.x), pmb, fmaf(fb, t0.w, t0.z) * prb);                                       \
-                Lb = fmaf(fmaf(fa, t2.w, t2.z), pma, fmaf(fa, t1.y, t1.x) * pra) +                                      \
-                     fmaf(fmaf(fb, t2.w, t2.z), pmb, fmaf(fb, t1.y, t1.x) * prb);                                       \
+                const P2 fa2 = bc(fa), fb2 = bc(fb);                                                                    \
+                Lrg = add2(fma2(fma2(fa2, Ms, Mi), bc(pma), mul2(fma2(fa2, Rs, Ri), bc(pra))),                          \
+                           fma2(fma2(fb2, Ms, Mi), bc(pmb), mul2(fma2(fb2, Rs, Ri), bc(prb))));                         \
+                Lb = fmaf(fmaf(fa, tb.w, tb.z), pma, fmaf(fa, tb.y, tb.x) * pra) +                                      \
+                     fmaf(fmaf(fb, tb.w, tb.z), pmb, fmaf(fb, tb.y, tb.x) * prb);                                       \
             } else {                          /* half sums: the texel's total is doubled after the loop */              \
-                float2 cr, cg, cb;                                                                                      \
-                tab3<SW32, (l) * L_STRIDE>(addr, tab_swap(ta), cr, cg, cb);                                             \
-                Lr = fmaf(fm, cr.y, cr.x); Lg = fmaf(fm, cg.y, cg.x); Lb = fmaf(fm, cb.y, cb.x);                        \
+                P2 irg, srg; float2 cb;                                                                                 \
+                tab3<SW32, (l) * L_STRIDE>(addr, tab_swap(ta), irg, srg, cb);                                           \
+                Lrg = fma2(bc(fm), srg, irg); Lb = fmaf(fm, cb.y, cb.x);                                                \
             }                                                                                                           \
             if (gnd) {                                                                                                  \
                 const float2 N = GN.n[blockIdx.z][(l) >= DL / 2 ? (l) - DL / 2 : 0];                                    \
@@ -641,16 +669,16 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                 const float ema = __fadd_rd(fmaf(qd, N.x, tem), MAGIC), emb = __fadd_rd(fmaf(qdn, N.x, tem), MAGIC);    \
                 if (ema != emb) straddle |= 0x10000u << (l);                      /* an irradiance knot between them */ \
                 const uint32_t ea = erow_t + (uint32_t)((l) - DL / 2) * grow_b + __float_as_uint(ema) * 24u;            \
-                const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);           \
+                const P2 ei = lds64p<GR_OFF>(ea), es = lds64p<GR_OFF + 8>(ea);                                          \
+                const float2 eb = lds64<GR_OFF + 16>(ea);                                                               \
                 if (ORDER2) {                                                                                           \
-                    Lr = fmaf(2.f, fmaf(tem, er.y, er.x), Lr);                                                          \
-                    Lg = fmaf(2.f, fmaf(tem, eg.y, eg.x), Lg);                                                          \
+                    Lrg = fma2(bc(2.f), fma2(bc(tem), es, ei), Lrg);                                                    \
                     Lb = fmaf(2.f, fmaf(tem, eb.y, eb.x), Lb);                                                          \
                 } else {                                                                                                \
-                    Lr += fmaf(tem, er.y, er.x); Lg += fmaf(tem, eg.y, eg.x); Lb += fmaf(tem, eb.y, eb.x);              \
+                    Lrg = add2(Lrg, fma2(bc(tem), es, ei)); Lb += fmaf(tem, eb.y, eb.x);                                \
                 }                                                                                                       \
             }                                                                                                           \
-            ar = fmaf(Lr, Wr[l], ar); ag = fmaf(Lg, Wg[l], ag); ab = fmaf(Lb, Wb[l], ab);                               \
+            arg = fma2(Lrg, Wrg[l], arg); ab = fmaf(Lb, Wb[l], ab);                                                     \
         }
         FB_PAIR_STEP(0) FB_PAIR_STEP(1) FB_PAIR_STEP(2) FB_PAIR_STEP(3)
         FB_PAIR_STEP(4) FB_PAIR_STEP(5) FB_PAIR_STEP(6) FB_PAIR_STEP(7)
@@ -660,16 +688,20 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
         // The rare sample b that sits beyond a knot was evaluated on a's segment: add (its own segment - a's segment) at
         // its coordinate.  A compact loop over the affected theta rows (run-time l: the weights come out of the register
         // file through a select chain); per-lane predicates only, so a texel's result does not depend on its partner.
+        float ar, ag;
+        upk(arg, ar, ag);
         {
             const uint32_t any = __reduce_or_sync(0xffffffffu, straddle);
             uint32_t steps = (any | (any >> 16)) & 0xffffu;
             while (steps) {
                 const int l = __ffs((int)steps) - 1;
                 steps &= steps - 1;
-                float wr = Wr[0], wg = Wg[0], wb = Wb[0];
+                P2 wrg = Wrg[0];
+                float wr, wg, wb = Wb[0];
 #pragma unroll
                 for (int j = 1; j < DL; ++j)
-                    if (l == j) { wr = Wr[j]; wg = Wg[j]; wb = Wb[j]; }
+                    if (l == j) { wrg = Wrg[j]; wb = Wb[j]; }
+                upk(wrg, wr, wg);
                 const float ct = CT16[l], st = ST16[l];
                 const float hs = ORDER2 ? 1.f : 0.5f;
                 float dr = 0.f, dg = 0.f, db = 0.f;
@@ -699,10 +731,11 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                     const uint32_t grow_l = erow_t + (uint32_t)(l - DL / 2) * grow_b;
                     const uint32_t ea = grow_l + __float_as_uint(__fadd_rd(fmaf(qd, N.x, tem), MAGIC)) * 24u;
                     const uint32_t eb_ = grow_l + __float_as_uint(__fadd_rd(teb, MAGIC)) * 24u;
-                    const float2 er = lds64<GR_OFF>(ea), eg = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);
-                    const float2 fr = lds64<GR_OFF>(eb_), fg = lds64<GR_OFF + 8>(eb_), fbb = lds64<GR_OFF + 16>(eb_);
-                    dr += hs * (fmaf(teb, fr.y, fr.x) - fmaf(teb, er.y, er.x));
-                    dg += hs * (fmaf(teb, fg.y, fg.x) - fmaf(teb, eg.y, eg.x));
+                    // ground-row entries: (red, green) intercepts, (red, green) slopes, blue (intercept, slope)
+                    const float2 ei = lds64<GR_OFF>(ea), es = lds64<GR_OFF + 8>(ea), eb = lds64<GR_OFF + 16>(ea);
+                    const float2 fi = lds64<GR_OFF>(eb_), fs = lds64<GR_OFF + 8>(eb_), fbb = lds64<GR_OFF + 16>(eb_);
+                    dr += hs * (fmaf(teb, fs.x, fi.x) - fmaf(teb, es.x, ei.x));
+                    dg += hs * (fmaf(teb, fs.y, fi.y) - fmaf(teb, es.y, ei.y));
                     db += hs * (fmaf(teb, fbb.y, fbb.x) - fmaf(teb, eb.y, eb.x));
                 }
                 ar = fmaf(dr, wr, ar); ag = fmaf(dg, wg, ag); ab = fmaf(db, wb, ab);
