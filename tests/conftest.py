@@ -51,6 +51,11 @@ SMOKE_DIMS = dict(scattering_r_size=8, scattering_mu_size=32, scattering_mu_s_si
 DUMP_DIMS = dict(scattering_r_size=16, scattering_mu_size=64, scattering_mu_s_size=16, scattering_nu_size=4)   # examples/dump.rs:101-107
 
 
+# neither powers of two nor multiples of a warp anywhere (tests/golden/reference_odd_f32.npz holds the reference's output)
+ODD_DIMS = dict(scattering_r_size=7, scattering_mu_size=22, scattering_mu_s_size=11, scattering_nu_size=3,
+                transmittance_mu_size=100, transmittance_r_size=33, irradiance_mu_s_size=20, irradiance_r_size=9)
+
+
 # a thin cut of the high-resolution config (BASELINE.json configs[2]: nu 32, mu_s 128): rows wider than one CTA
 WIDE_DIMS = dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=64, scattering_nu_size=32, order=3)
 
@@ -69,7 +74,9 @@ def oracle_tall_f32():
 @pytest.fixture(scope="session")
 def oracle_wide_f32():
     from oracle import oracle as O
-    return O.precompute(O.Params(**WIDE_DIMS), O.F32, keep_history=True)
+    t = O.precompute(O.Params(**WIDE_DIMS), O.F32, keep_history=True)
+    assert_equals_reference_golden(t, "reference_wide_f32.npz")
+    return t
 
 
 @pytest.fixture(scope="session")
@@ -102,7 +109,7 @@ def assert_equals_reference_golden(tables, fixture: str):
     assert np.array_equal(pick(tables.scattering).astype(np.float16), g["scattering"])
     assert np.array_equal(pick(tables.delta_rayleigh).astype(np.float16), g["delta_rayleigh"])
     assert np.array_equal(pick(tables.delta_mie).astype(np.float16), g["delta_mie"])
-    for order in (2, 3, 4):
+    for order in sorted(int(k[1]) for k in g.files if k.endswith("_scattering_density")):
         h = tables.history[order]
         for k in ("scattering_density", "delta_multiple_scattering", "scattering"):
             assert np.array_equal(pick(h[k]).astype(np.float16), g[f"o{order}_{k}"]), (fixture, order, k)

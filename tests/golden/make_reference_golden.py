@@ -8,6 +8,11 @@
   reference_default_f32.npz  default dims (Parameters::default(), 4 orders; BASELINE.json configs[1]): transmittance,
                              irradiance and every delta_irradiance in full, 4096 seeded texels of every 3-D table of every
                              order (the sky evaluation is pinned at the smoke dims, where the full tables fit a fixture)
+  reference_odd_f32.npz      dims that are neither powers of two nor multiples of a warp (nu 3, mu_s 11, mu 22, r 7,
+                             transmittance 100x33, irradiance 20x9), 4 orders: every table of every order in full
+  reference_wide_f32.npz     rows of 2048 texels with 32 nu knots (r 4, mu 8, mu_s 64, nu 32), 3 orders: the 2-D tables in
+                             full, 4096 seeded texels of every 3-D table (the bank-swizzled density tables and the
+                             multi-texel-per-thread row kernels of the high-resolution configuration run at these dims)
 Values are stored in the reference's storage formats (float32 / float16), which hold them exactly.
 """
 import os
@@ -27,13 +32,18 @@ SMOKE_DIMS = dict(scattering_r_size=8, scattering_mu_size=32, scattering_mu_s_si
 VIEWS_SMALL = (3, 11, 13)
 
 
-def tables(t, idx=None):
+ODD_DIMS = dict(scattering_r_size=7, scattering_mu_size=22, scattering_mu_s_size=11, scattering_nu_size=3,
+                transmittance_mu_size=100, transmittance_r_size=33, irradiance_mu_s_size=20, irradiance_r_size=9)
+WIDE_DIMS = dict(scattering_r_size=4, scattering_mu_size=8, scattering_mu_s_size=64, scattering_nu_size=32, order=3)
+
+
+def tables(t, idx=None, orders=(2, 3, 4)):
     pick = (lambda a: a) if idx is None else (lambda a: a.reshape(-1, 4)[idx])
     out = dict(transmittance=t.transmittance.astype(np.float32), irradiance=t.irradiance.astype(np.float32),
                direct_irradiance=t.history["single"]["delta_irradiance"].astype(np.float32),
                scattering=pick(t.scattering).astype(np.float16), delta_rayleigh=pick(t.delta_rayleigh).astype(np.float16),
                delta_mie=pick(t.delta_mie).astype(np.float16), scattering_single=pick(t.history["single"]["scattering"]).astype(np.float16))
-    for order in (2, 3, 4):
+    for order in orders:
         h = t.history[order]
         out[f"o{order}_scattering_density"] = pick(h["scattering_density"]).astype(np.float16)
         out[f"o{order}_delta_multiple_scattering"] = pick(h["delta_multiple_scattering"]).astype(np.float16)
@@ -43,9 +53,24 @@ def tables(t, idx=None):
     return out
 
 
+def more_dims(t0):
+    po = O.Params(**ODD_DIMS)
+    np.savez_compressed(os.path.join(HERE, "reference_odd_f32.npz"), **tables(R.precompute(po, keep_history=True)))
+    print("odd dims done", time.time() - t0)
+    pw = O.Params(**WIDE_DIMS)
+    w = R.precompute(pw, keep_history=True)
+    idx = np.sort(np.random.default_rng(4321).choice(int(np.prod(pw.s_shape[:3])), 4096, replace=False)).astype(np.int64)
+    g = tables(w, idx, orders=(2, 3))
+    g["idx"] = idx
+    np.savez_compressed(os.path.join(HERE, "reference_wide_f32.npz"), **g)
+    print("wide dims done", time.time() - t0)
+
+
 def main():
     assert R.build(), "the reference checkout (/root/reference/shaders) is needed to generate these fixtures"
     t0 = time.time()
+    if sys.argv[1:] == ["extra"]:               # only the two fixtures added later
+        return more_dims(t0)
     ps = O.Params(**SMOKE_DIMS)
     s = R.precompute(ps, keep_history=True)
     out = tables(s)
@@ -67,6 +92,7 @@ def main():
     g["idx"] = idx
     np.savez_compressed(os.path.join(HERE, "reference_default_f32.npz"), **g)
     print("wrote fixtures", time.time() - t0)
+    more_dims(t0)
 
 
 if __name__ == "__main__":

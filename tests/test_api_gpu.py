@@ -1,5 +1,6 @@
 """GPU tests of the C-ABI object model: batches, error codes, lifetimes, host-buffer entry points."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -225,3 +226,40 @@ def test_slow_stage_cliffs_are_reported():
     pend.wait()
     assert pend.slow_stages() == 1 << api.STAGE_SCATTERING_DENSITY
     assert fb.Atmosphere.build(fb.Builder(0), None, fb.Parameters(**SMOKE_DIMS)).slow_stages() == 0
+
+
+def test_external_semaphore_wrappers_reject_what_is_not_a_semaphore():
+    """fb_external_semaphore_*  wrap cudaImportExternalSemaphore / Signal / Wait for the timeline
+    semaphore a Vulkan caller exports.  No Vulkan loader exists in this image, so what can be executed is the error
+    contract: a descriptor that is not a semaphore is refused with a status (no handle comes back, nothing crashes),
+    NULL handles are invalid arguments, destroy(NULL) is a no-op.  Run in a child process so that a driver that reacts
+    badly to the bogus descriptor cannot take the other tests' context with it."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import os, ctypes
+        from ctypes import byref, c_void_p
+        import fuzzyblue_b200 as fb
+        from fuzzyblue_b200 import api
+        lib = api._lib()
+        b = fb.Builder(0)
+        h = c_void_p()
+        INVALID = 1                                   # FB_ERR_INVALID_ARGUMENT, include/fuzzyblue.h
+        assert lib.fb_external_semaphore_import_fd(0, -1, 1, byref(h)) == INVALID and not h.value
+        r, w = os.pipe()
+        st = lib.fb_external_semaphore_import_fd(0, r, 1, byref(h))
+        assert st != api.FB_OK and not h.value, st
+        assert lib.fb_last_error() is not None
+        os.close(w)
+        try: os.close(r)
+        except OSError: pass
+        assert lib.fb_external_semaphore_signal(None, 1, None) == INVALID
+        assert lib.fb_external_semaphore_wait(None, 1, None) == INVALID
+        lib.fb_external_semaphore_destroy(None)
+        # the context still works
+        T, S, E = fb.precompute_host(b, fb.Parameters(scattering_r_size=2, scattering_mu_size=4, scattering_mu_s_size=4, scattering_nu_size=2, order=2))
+        assert float(T.max()) > 0
+        print("SEMAPHORE-CONTRACT-OK")
+    """)
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "SEMAPHORE-CONTRACT-OK" in out.stdout, (out.stdout[-500:], out.stderr[-1500:])

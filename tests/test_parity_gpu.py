@@ -429,6 +429,23 @@ def test_cuda_against_the_reference_golden_vectors(default_tables, builder, fami
         check_compounded(name + " vs reference", err16(default_tables[name].reshape(-1, 4)[idx], g[name]), max_count=SMALL_TABLE_OUTLIERS)
 
 
+def test_cuda_against_the_reference_golden_vectors_odd_and_wide_dims(builder, family):
+    """The same against tests/golden/reference_odd_f32.npz (no size a power of two or a multiple of a warp; every table
+    in full) and reference_wide_f32.npz (rows of 2048 texels, 32 nu knots: the bank-swizzled density tables and the
+    multi-texel-per-thread row kernels of the high-resolution configuration; 4096 seeded texels)."""
+    from .conftest import ODD_DIMS
+    g = np.load(os.path.join(GOLDEN, "reference_odd_f32.npz"))
+    T, S, E = fb.precompute_host(builder, fb.Parameters(**ODD_DIMS))
+    check("odd transmittance vs reference", err32(T, g["transmittance"]))
+    check("odd irradiance vs reference", err32(E, g["irradiance"]))
+    check_compounded("odd scattering vs reference", err16(S, g["scattering"]), max_count=SMALL_TABLE_OUTLIERS)
+    g = np.load(os.path.join(GOLDEN, "reference_wide_f32.npz"))
+    T, S, E = fb.precompute_host(builder, fb.Parameters(**WIDE_DIMS))
+    check("wide transmittance vs reference", err32(T, g["transmittance"]))
+    check("wide irradiance vs reference", err32(E, g["irradiance"]))
+    check_compounded("wide scattering vs reference", err16(S.reshape(-1, 4)[g["idx"]], g["scattering"]), max_count=SMALL_TABLE_OUTLIERS)
+
+
 def test_default_dims_properties(default_tables):
     """Size-independent properties at the full default dims (BASELINE.json configs[1])."""
     T, E = default_tables["transmittance"], default_tables["irradiance"]
