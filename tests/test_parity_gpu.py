@@ -446,6 +446,25 @@ def test_cuda_against_the_reference_golden_vectors_odd_and_wide_dims(builder, fa
     check_compounded("wide scattering vs reference", err16(S.reshape(-1, 4)[g["idx"]], g["scattering"]), max_count=SMALL_TABLE_OUTLIERS)
 
 
+def test_product_outputs_are_bit_stable(family):
+    """Change detector (not a parity reference): the product path's tables at three dims and two rendered views hash to
+    what tests/golden/cuda_hashes.json recorded on a B200 (tests/golden/make_cuda_hashes.py).  The round-2 optimisations
+    that claim bit-identical output were settled by this kind of hash A/B; a change meant to alter bits regenerates the
+    file."""
+    import importlib.util
+    import json
+    path = os.path.join(GOLDEN, "cuda_hashes.json")
+    if family != "fast" or not os.path.exists(path):
+        pytest.skip("hashes are recorded for the product (FAST) kernels")
+    spec = importlib.util.spec_from_file_location("make_cuda_hashes", os.path.join(GOLDEN, "make_cuda_hashes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(path) as f:
+        want = json.load(f)
+    got = mod.compute()
+    assert got == want, {k: (got[k], want.get(k)) for k in got if got[k] != want.get(k)}
+
+
 def test_default_dims_properties(default_tables):
     """Size-independent properties at the full default dims (BASELINE.json configs[1])."""
     T, E = default_tables["transmittance"], default_tables["irradiance"]
