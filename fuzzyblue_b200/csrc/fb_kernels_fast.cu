@@ -98,7 +98,7 @@ __device__ constexpr float ST16[DL] = {0.0980171412f, 0.290284663f, 0.471396744f
 //   order >= 3 entry, 24 B:  [R.r dR.r | R.g dR.g | R.b dR.b]                              3 x LDS.64
 //   order 2    entry, 48 B:  [R.r dR.r R.g dR.g | R.b dR.b M.r dM.r | M.g dM.g M.b dM.b]   3 x LDS.128
 #ifndef FB_PAIR_O2
-#define FB_PAIR_O2 0
+#define FB_PAIR_O2 1   // round 1 measured the order-2 pair body slower; with the packed (red, green) channels it wins: 936 -> 904 us (64-bit / 128-bit loads only, see PAIRED)
 #endif
 #ifndef FB_PAIR_O3
 #define FB_PAIR_O3 1
@@ -341,7 +341,9 @@ k_density_main(const __grid_constant__ FbParams P, const __grid_constant__ Trig 
                ) {
     typedef DensityCfg<ORDER2> C;
     constexpr int ENT = C::ENT, TT = C::T, NWARPS = C::NWARPS;
-    constexpr bool PAIRED = C::PAIRED;
+    // order 2 with bank-swizzled tables (32-bit loads) keeps the general body: there the pair body measured slower
+    // (high-resolution dims, 16 levels: 31.5 -> 32.7 ms)
+    constexpr bool PAIRED = C::PAIRED && !(ORDER2 && SW32);
     constexpr int ENT_B = ENT * 4;                       // bytes per table entry
     constexpr int L_STRIDE = TT * ENT_B;                 // bytes per theta row block
     constexpr int TAB_B = DL * L_STRIDE;                 // 96 KiB
