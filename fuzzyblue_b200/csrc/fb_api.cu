@@ -372,6 +372,8 @@ struct FbRenderer {
     int kernels;
     void* sweep_draws;           // device copy of a sweep's draw parameters + per-view constants
     uint32_t sweep_capacity;
+    void* view_tables;           // per-view sky tables of the FAST path (fb_render.cu: k_view_tables), rewritten by every draw
+    size_t view_tables_bytes;
     // the FAST path's expanded copy of one atmosphere's scattering table (fb_render.cu: Tex3X), rebuilt when a draw
     // names other table contents; draws on other streams wait for the rebuild through `expanded_ready`
     void* expanded;
@@ -1085,6 +1087,7 @@ int fb_renderer_create(FbBuilder* b, FbRenderer** out) {
     r->kernels = b->kernels;
     r->sweep_draws = nullptr;
     r->sweep_capacity = 0;
+    r->view_tables = nullptr; r->view_tables_bytes = 0;
     r->expanded = nullptr; r->expanded_bytes = 0; r->expanded_serial = 0; r->expanded_version = 0; r->expanded_ready = nullptr;
     r->no_expand = std::getenv("FUZZYBLUE_B200_RENDER_FP16_TABLE") != nullptr;
     r->draws = std::make_shared<Completion>();
@@ -1095,6 +1098,7 @@ void fb_renderer_destroy(FbRenderer* r) {
     if (!r) return;
     DeviceGuard g(r->device);
     cudaFree(r->sweep_draws);
+    cudaFree(r->view_tables);
     cudaFree(r->expanded);
     if (r->expanded_ready) cudaEventDestroy(r->expanded_ready);
     delete r;
@@ -1141,7 +1145,21 @@ static int draw_common(FbRenderer* r, const FbAtmosphere* a, const FbDrawParams*
         }
         expanded = r->expanded;
     }
-    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, expanded, d, views > 1 ? r->sweep_draws : nullptr, views, depth,
+    // Per-view sky tables: scratch the draw's pre-pass rewrites.  A draw on another stream may still be reading the previous
+    // contents (and a sweep's view records): wait for it on the device, as a table rebuild does.
+    void* vtabs = nullptr;
+    if (r->kernels != FB_KERNELS_REFERENCE) {
+        const size_t need = (size_t)views * render_view_table_bytes(a->P);
+        if (r->view_tables_bytes < need) {
+            cudaFree(r->view_tables);                       // synchronises the device: no earlier draw still reads it
+            r->view_tables = nullptr; r->view_tables_bytes = 0;
+            FB_CUDA(cudaMalloc(&r->view_tables, need));
+            r->view_tables_bytes = need;
+        }
+        FB_CUDA(r->draws->stream_wait((cudaStream_t)stream));
+        vtabs = r->view_tables;
+    }
+    cudaError_t e = render_sky(a->P, a->transmittance, a->scattering, expanded, d, views > 1 ? r->sweep_draws : nullptr, vtabs, views, depth,
                                (float4*)color, (float4*)transm, (float4*)blend, w, h, r->kernels, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "render_sky launch");
     r->draws->note((cudaStream_t)stream);

@@ -75,9 +75,12 @@ size_t render_view_record_bytes();
 size_t render_expanded_bytes(const FbParams& P);
 cudaError_t render_expand_scattering(const FbParams& P, const float4* transmittance, const uint2* scattering, void* expanded,
                                      cudaStream_t s);
+// `view_tables_dev` (may be NULL): views * render_view_table_bytes() of device scratch for the per-view sky tables of the
+// FAST path (fb_render.cu: k_view_tables), rewritten by every call.
+size_t render_view_table_bytes(const FbParams& P);
 cudaError_t render_sky(const FbParams& P, const float4* transmittance, const uint2* scattering, const void* expanded,
-                       const FbDrawParams* draws_host, void* view_records_dev, uint32_t views, const float* depth, float4* color, float4* transm,
-                       float4* blend_fb, uint32_t w, uint32_t h, int kernels, cudaStream_t s);
+                       const FbDrawParams* draws_host, void* view_records_dev, void* view_tables_dev, uint32_t views, const float* depth,
+                       float4* color, float4* transm, float4* blend_fb, uint32_t w, uint32_t h, int kernels, cudaStream_t s);
 cudaError_t sky_radiance(const FbParams& P, const float4* transmittance, const uint2* scattering, const float* cam,
                          const float* view, const float* sun, uint64_t n, float* radiance, float* transm, cudaStream_t s);
 cudaError_t sun_sky_irradiance(const FbParams& P, const float4* transmittance, const float4* irradiance, const float* point,
