@@ -92,11 +92,14 @@ __device__ constexpr float ST16[DL] = {0.0980171412f, 0.290284663f, 0.471396744f
 // Texels per CTA are a compile-time constant so that every table offset inside the unrolled theta loop is an
 // immediate: 256 texels at order >= 3 (one look-up table), 128 at order 2 (Rayleigh + Mie tables): 96 KiB either way.
 //
-// Table entries are (value, delta-to-next-knot) pairs per channel, so the nu interpolation is one FFMA per channel and
+// Table entries are (intercept, slope) pairs per channel, so the nu interpolation is one FFMA per channel and
 // a sample reads exactly the 6 (12 at order 2) words it needs: the shared-memory data pipe is the binding unit of this
-// kernel and an LDS costs one wavefront per 4 bytes per lane whatever the address pattern (tools/lds_bench.cu).
-//   order >= 3 entry, 24 B:  [R.r dR.r | R.g dR.g | R.b dR.b]                              3 x LDS.64
-//   order 2    entry, 48 B:  [R.r dR.r R.g dR.g | R.b dR.b M.r dM.r | M.g dM.g M.b dM.b]   3 x LDS.128
+// kernel and an LDS costs one wavefront per 4 bytes per lane (tools/lds_bench.cu; the cheaper path the pipe has for
+// quads of lanes reading x,x,y,y or x,y,x,y -- tools/lds_pair_bench.cu -- is out of reach of a lane = phi staircase).
+// The red and green channels travel as the two halves of one 64-bit operand (packed fp32 pairs, FFMA2: see P2 below):
+//   order >= 3 entry, 24 B:  [i.r i.g | s.r s.g | i.b s.b]                                   3 x LDS.64
+//   order 2    entry, 48 B:  [Ri.r Ri.g Rs.r Rs.g | Mi.r Mi.g Ms.r Ms.g | Ri.b Rs.b Mi.b Ms.b]  3 x LDS.128
+// (i = intercept, s = slope of the nu segment; R = Rayleigh, M = Mie table)
 #ifndef FB_PAIR_O2
 #define FB_PAIR_O2 1   // round 1 measured the order-2 pair body slower; with the packed (red, green) channels it wins: 936 -> 904 us (64-bit / 128-bit loads only, see PAIRED)
 #endif

@@ -265,8 +265,11 @@ FB_API int fb_precompute_host(FbBuilder* b, const FbParams* p, uint32_t order, v
  * up to 256 MiB; bit-identical look-ups at half the instructions).  The expansion is re-derived when a draw names other
  * table contents (the rebuild waits on the device for earlier draws, no host synchronisation), so alternate between
  * atmospheres with one renderer each.
- * As with the reference's Renderer (descriptor sets per frame, render.rs:34-40), draws through one renderer are
- * externally synchronised by the caller. */
+ * A draw also writes small per-view tables (the look-ups of sky pixels that depend on the camera alone, blended once
+ * per view) into scratch the renderer owns; a draw therefore waits, on the device, for the renderer's earlier draws on
+ * other streams: draws through ONE renderer execute in submission order.  Use one renderer per stream to overlap draws.
+ * As with the reference's Renderer (descriptor sets per frame, render.rs:34-40), calls on one renderer are externally
+ * synchronised by the caller. */
 FB_API int fb_renderer_create(FbBuilder* b, FbRenderer** out);
 FB_API void fb_renderer_destroy(FbRenderer* r);
 /* Renderer::draw, src/render.rs:209-236 + shaders/render_sky.frag:24-35, one thread per pixel.
