@@ -82,6 +82,24 @@ def test_sky_evaluation_bit_for_bit_over_the_sweep():
     assert n_nan > 0 and n_ground > 1000
 
 
+def test_sky_evaluation_bit_for_bit_with_three_nu_knots():
+    """The same with a nu axis that is not a power of two (x / nu_size is then a true division in scattering.h:149-151) and
+    odd sizes everywhere: 8 views of the sweep on the odd-dims tables."""
+    from fuzzyblue_b200 import synthetic
+    from .conftest import ODD_DIMS
+    p = O.Params(**ODD_DIMS)
+    t = O.precompute(p, O.F32)
+    W, H = 64, 36
+    draws, extra = synthetic.camera_sweep(24, W, H)
+    for k in (0, 3, 5, 9, 11, 13, 17, 22):
+        depth = synthetic.analytic_depth(extra[k][0], extra[k][1], W, H)
+        d = O.pack_draw(draws[k].inverse_viewproj, draws[k].camera_position, draws[k].sun_direction)
+        oc, ot = O.render(p, O.F32, t.transmittance, t.scattering, d, depth)
+        rc, rt = R.render(p, t.transmittance, t.scattering, d, depth)
+        same(oc, rc, f"view {k} colour")
+        same(ot, rt, f"view {k} transmittance")
+
+
 def test_default_dims_stages_on_sampled_texels_bit_for_bit():
     """BASELINE.json configs[1] dims: each 3-D stage on 1024 seeded texels of the full-size tables (identical inputs)."""
     p = O.Params()
@@ -118,3 +136,10 @@ def test_committed_golden_vectors_are_what_the_reference_produces():
     assert np.array_equal(t.scattering.astype(np.float16), g["scattering"])
     assert np.array_equal(t.irradiance.astype(np.float32), g["irradiance"])
     assert np.array_equal(t.history[3]["scattering_density"].astype(np.float16), g["o3_scattering_density"])
+    from .conftest import ODD_DIMS, WIDE_DIMS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_odd_f32.npz"))
+    t = R.precompute(O.Params(**ODD_DIMS), keep_history=True)
+    assert np.array_equal(t.scattering.astype(np.float16), g["scattering"]) and np.array_equal(t.irradiance.astype(np.float32), g["irradiance"])
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_wide_f32.npz"))
+    t = R.precompute(O.Params(**WIDE_DIMS), keep_history=True)
+    assert np.array_equal(t.scattering.reshape(-1, 4)[g["idx"]].astype(np.float16), g["scattering"])
