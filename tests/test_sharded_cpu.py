@@ -184,3 +184,70 @@ def test_two_rank_sharded_precompute_equals_single_process(tmp_path, order, pipe
     assert np.array_equal(r0[:2], ref.delta_multiple_scattering[:2])
     assert np.array_equal(r0[2], prev.delta_multiple_scattering[2])
     assert np.all(np.isnan(r0[3]))
+
+
+def _simulate(world, order, dims, flags):
+    """All ranks of a world in ONE process: each rank runs its stage steps up to its next exchange; when every rank waits at
+    the same exchange it is carried out between the ranks' images (the semantics of sharded.GlooExecutor / the NCCL
+    executor: all-gather of sub-slabs, one-slice halos with the neighbours, rows broadcast from their owner)."""
+    p = fb.Parameters(order=order, **dims)
+    plans = [sharded.plan(p, r, world, flags) for r in range(world)]
+    be = [OracleBackend(O.Params(order=order, **dims)) for _ in range(world)]
+    n = p.scattering_r_size // world
+    pc = [0] * world
+    exchanges = 0
+    while True:
+        for r in range(world):
+            while pc[r] < len(plans[r]) and plans[r][pc[r]].op in (sharded.SHARD_STAGE, sharded.SHARD_JOIN):
+                s = plans[r][pc[r]]
+                if s.op == sharded.SHARD_STAGE:
+                    be[r].run_stage(s.stage, s.order, s.begin, s.end)
+                pc[r] += 1
+        if all(pc[r] == len(plans[r]) for r in range(world)):
+            break
+        heads = [plans[r][pc[r]] for r in range(world)]          # a rank that has finished while others wait = deadlock
+        key = lambda s: (s.op, s.image, s.begin, s.end, s.root)
+        assert all(key(h) == key(heads[0]) for h in heads), [repr(h) for h in heads]
+        s = heads[0]
+        if s.op == sharded.SHARD_ALLGATHER:
+            for q in range(world):
+                src = be[q].tensor(s.image)[q * n + s.begin:q * n + s.end].clone()
+                for r in range(world):
+                    if r != q:
+                        be[r].tensor(s.image)[q * n + s.begin:q * n + s.end] = src
+        elif s.op == sharded.SHARD_HALO:
+            first = [be[r].tensor(s.image)[r * n].clone() for r in range(world)]
+            last = [be[r].tensor(s.image)[(r + 1) * n - 1].clone() for r in range(world)]
+            for r in range(world):
+                if r > 0:
+                    be[r].tensor(s.image)[r * n - 1] = last[r - 1]
+                if r < world - 1:
+                    be[r].tensor(s.image)[(r + 1) * n] = first[r + 1]
+        elif s.op == sharded.SHARD_BCAST_ROWS:
+            src = be[s.root].tensor(s.image)[s.begin:s.end].clone()
+            for r in range(world):
+                if r != s.root:
+                    be[r].tensor(s.image)[s.begin:s.end] = src
+        else:
+            raise AssertionError(s.op)
+        exchanges += 1
+        for r in range(world):
+            pc[r] += 1
+    return be, exchanges
+
+
+@pytest.mark.parametrize("world,pipelined,r_size,order", [(4, False, 8, 3), (8, False, 8, 3), (8, True, 8, 3), (4, True, 16, 4), (8, False, 16, 4)])
+def test_simulated_worlds_of_4_and_8_equal_single_process(world, pipelined, r_size, order):
+    """The plan for 4 and 8 ranks (what the 8-GPU runs execute), with fewer irradiance rows than ranks at world 8 and one
+    altitude level per rank: every slab a rank never computes starts as NaN, and every rank must end with the single-process
+    tables, exactly.  (World 2 runs through real gloo processes above.)"""
+    dims = dict(DIMS, scattering_r_size=r_size)
+    flags = sharded.GATHER_RESULT | (sharded.PIPELINE_ALWAYS if pipelined else 0)
+    be, exchanges = _simulate(world, order, dims, flags)
+    ref = O.precompute(O.Params(order=order, **dims), O.F32)
+    for r in range(world):
+        assert np.array_equal(be[r]._np(api.IMAGE_TRANSMITTANCE), ref.transmittance)
+        assert np.array_equal(be[r]._np(api.IMAGE_IRRADIANCE), ref.irradiance), r
+        assert np.array_equal(be[r]._np(api.IMAGE_SCATTERING), ref.scattering), r
+    assert sum(b.rows_computed for b in be) == (order - 1) * dims["irradiance_r_size"]     # each row once per order
+    assert exchanges > 0
