@@ -908,7 +908,7 @@ int fb_pending_run_stage(FbPending* p, int stage, uint32_t order, uint32_t r_beg
 }
 uint32_t fb_pending_slow_stages(const FbPending* p) { return p ? p->slow_stages : 0; }
 uint32_t fb_params_slow_stages(const FbParams* p) {
-    if (!p) return 0;
+    if (!p || fb_params_validate(p) != FB_OK) return 0;     // nothing runs with such a block: fb_params_validate says why
     uint32_t m = 0;
     if (!fast::density_is_fast(*p)) m |= 1u << FB_STAGE_SCATTERING_DENSITY;
     if (!fast::multiple_is_fast(*p)) m |= 1u << FB_STAGE_MULTIPLE_SCATTERING;

@@ -1374,7 +1374,7 @@ static int multiple_chunk(int W) {
 }
 bool multiple_is_fast(const FbParams& P) {
     const int W = P.scattering_nu_size * P.scattering_mu_s_size;
-    if (W > 8192 || P.scattering_mu_s_size < 2) return false;
+    if (W <= 0 || W > 8192 || P.scattering_mu_s_size < 2) return false;   // W <= 0: a block fb_params_validate rejects
     return sizeof(MultiNode) * NS + (size_t)multiple_chunk(W) * W * sizeof(float4) <= 200 * 1024;
 }
 

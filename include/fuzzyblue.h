@@ -146,7 +146,8 @@ FB_API int fb_params_validate(const FbParams* p);
 /* Bit s (FbStage) is set when stage s of these dims is NOT covered by the restructured kernels and runs the
  * one-thread-per-texel transcription instead (~30x slower): scattering_density for scattering_nu_size > 128 or
  * irradiance_mu_s_size > 512, multiple_scattering for rows of more than 8192 texels.  0 for every config of
- * BASELINE.json.  fb_pending_slow_stages reports what a pending actually ran. */
+ * BASELINE.json, and 0 for a block fb_params_validate rejects (nothing runs with it).  fb_pending_slow_stages reports
+ * what a pending actually ran. */
 FB_API uint32_t fb_params_slow_stages(const FbParams* p);
 
 /* Builder::new, src/precompute.rs:61-68: one-time, device-wide setup.  `device` is a CUDA ordinal. */
