@@ -73,3 +73,57 @@ def test_every_accepted_plan_tiles_the_r_axis_and_agrees_on_its_exchanges(world,
     rows = sorted((s.begin, s.end) for pl in plans for s in pl
                   if s.op == sharded.SHARD_STAGE and s.stage == api.STAGE_INDIRECT_IRRADIANCE and s.order == 1)
     assert rows[0][0] == 0 and rows[-1][1] == p.irradiance_r_size and all(rows[i][1] == rows[i + 1][0] for i in range(len(rows) - 1))
+
+
+@settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(st.binary(min_size=320, max_size=320), st.integers(0, 9), st.integers(0, 8), st.integers(1, 8))
+def test_any_320_bytes_are_answered_with_a_status(blob, order, rank, world):
+    """The parameter block is plain bytes from the caller (a uniform buffer in the reference): ANY 320 bytes get a status
+    from every host-only entry point, and a block that validates has sizes in range and finite geometry."""
+    lib = api._lib()
+    p = api.FbParams()
+    assert ctypes.sizeof(p) == 320
+    ctypes.memmove(byref(p), blob, 320)
+    ok = lib.fb_params_validate(byref(p))
+    assert ok in (api.FB_OK, 1)
+    ext, e2, n = api.FbExtent3D(), api.FbExtent2D(), c_uint32(0)
+    for st_ in (lib.fb_params_scattering_extent(byref(p), byref(ext)), lib.fb_params_transmittance_extent(byref(p), byref(e2)),
+                lib.fb_params_irradiance_extent(byref(p), byref(e2)), lib.fb_sharded_plan(byref(p), order, rank, world, 1, None, 0, byref(n))):
+        assert st_ in (api.FB_OK, 1)
+    lib.fb_params_slow_stages(byref(p))
+    if ok == api.FB_OK:
+        sizes = (p.transmittance_mu_size, p.transmittance_r_size, p.scattering_r_size, p.scattering_mu_size, p.scattering_mu_s_size,
+                 p.scattering_nu_size, p.irradiance_mu_s_size, p.irradiance_r_size)
+        assert all(2 <= v <= 16384 for v in sizes)
+        assert math.isfinite(p.bottom_radius) and math.isfinite(p.top_radius) and 0 < p.bottom_radius < p.top_radius
+        assert -1.0 <= p.mu_s_min <= 0.0 and abs(p.mie_phase_function_g) < 1.0
+
+
+def test_a_valid_block_with_one_poisoned_float_is_rejected():
+    """Every float of the block, one at a time, as NaN and as +inf: fb_params_validate must refuse (the restructured
+    kernels address shared memory from geometry without per-sample clamps)."""
+    lib = api._lib()
+    base = fb.Parameters().raw()
+    assert lib.fb_params_validate(byref(base)) == api.FB_OK
+    int_fields = {"transmittance_mu_size", "transmittance_r_size", "scattering_r_size", "scattering_mu_size", "scattering_mu_s_size",
+                  "scattering_nu_size", "irradiance_mu_s_size", "irradiance_r_size"}
+    raw = bytes(base)
+    ints = set()
+    for name, _ in api.FbParams._fields_:
+        if name in int_fields:
+            off = getattr(api.FbParams, name).offset
+            ints.update(range(off, off + 4))
+    import struct
+    refused = 0
+    for off in range(0, 320, 4):
+        if off in ints:
+            continue
+        if struct.unpack_from("<f", raw, off)[0] == 0.0 and off not in {getattr(api.FbParams, n).offset for n, _ in api.FbParams._fields_}:
+            pass                                                  # padding words are zero in a default block; poisoning them must not matter
+        for bad in (float("nan"), float("inf")):
+            blob = bytearray(raw)
+            struct.pack_into("<f", blob, off, bad)
+            p = api.FbParams()
+            ctypes.memmove(byref(p), bytes(blob), 320)
+            refused += lib.fb_params_validate(byref(p)) != api.FB_OK
+    assert refused >= 2 * 40                                       # the block holds more than 40 meaningful floats
